@@ -1,0 +1,239 @@
+"""ctypes binding of include/lbm.h (liblbm_b200.so) — what tests/ and bench.py call.
+
+There is no fallback: if the CUDA library is missing or no GPU is visible the calls
+raise ``LbmError`` (the product path never routes through oracle/ or any CPU code).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .decks import NSPEEDS, Params
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "liblbm_b200.so")
+
+# every symbol include/lbm.h declares (checked by tests/test_cabi_symbols.py)
+EXPORTS = [
+    "lbm_create", "lbm_create_on", "lbm_create_slab", "lbm_partition_rows", "lbm_export_size", "lbm_export",
+    "lbm_connect", "lbm_destroy", "lbm_upload", "lbm_halo_push", "lbm_download_cells", "lbm_download_av_vels",
+    "lbm_download_av_sums", "lbm_combine_av_sums", "lbm_host_alloc", "lbm_host_free", "lbm_run", "lbm_sync",
+    "lbm_run_timed", "lbm_set_option", "lbm_get_info", "lbm_device_count", "lbm_abi_version", "lbm_last_error",
+]
+
+
+class LbmError(RuntimeError):
+    pass
+
+
+class LbmParams(C.Structure):
+    """lbm_params == t_param (d2q9-bgk.c:81-92)."""
+    _fields_ = [("density", C.c_float), ("accel", C.c_float), ("omega", C.c_float),
+                ("free_cells_inv", C.c_float), ("nx", C.c_int), ("ny", C.c_int),
+                ("maxIters", C.c_int), ("reynolds_dim", C.c_int)]
+
+
+class LbmInfo(C.Structure):
+    _fields_ = [("abi_version", C.c_int), ("nslabs", C.c_int), ("rank", C.c_int), ("nranks", C.c_int),
+                ("y0", C.c_int), ("rows", C.c_int), ("pitch", C.c_int), ("cells_per_thread", C.c_int),
+                ("threads_per_block", C.c_int), ("streaming", C.c_int), ("steps_per_launch", C.c_int),
+                ("steps_done", C.c_longlong), ("kernel_launches", C.c_longlong),
+                ("partials_per_step", C.c_longlong), ("kernel_name", C.c_char * 64)]
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen the in-tree library and declare the prototypes.  Raises LbmError if absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise LbmError(f"{path} is not built — run `make` (or __graft_entry__.build()) first")
+    lib = C.CDLL(path)
+    vp, fp, ip, dp = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)
+    PP = C.POINTER(LbmParams)
+    lib.lbm_create.argtypes = [C.POINTER(vp), PP, C.c_int]
+    lib.lbm_create_on.argtypes = [C.POINTER(vp), PP, C.c_int, ip]
+    lib.lbm_create_slab.argtypes = [C.POINTER(vp), PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.lbm_partition_rows.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip]
+    lib.lbm_partition_rows.restype = None
+    lib.lbm_export_size.argtypes = []
+    lib.lbm_export_size.restype = C.c_size_t
+    lib.lbm_export.argtypes = [vp, vp]
+    lib.lbm_connect.argtypes = [vp, vp, vp]
+    lib.lbm_destroy.argtypes = [vp]
+    lib.lbm_destroy.restype = None
+    lib.lbm_upload.argtypes = [vp, vp, vp]
+    lib.lbm_halo_push.argtypes = [vp]
+    lib.lbm_download_cells.argtypes = [vp, vp]
+    lib.lbm_download_av_vels.argtypes = [vp, fp, C.c_int]
+    lib.lbm_download_av_sums.argtypes = [vp, dp, dp, C.c_int]
+    lib.lbm_combine_av_sums.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_float, fp]
+    lib.lbm_combine_av_sums.restype = None
+    lib.lbm_host_alloc.argtypes = [C.c_size_t]
+    lib.lbm_host_alloc.restype = vp
+    lib.lbm_host_free.argtypes = [vp]
+    lib.lbm_host_free.restype = None
+    lib.lbm_run.argtypes = [vp, C.c_int]
+    lib.lbm_sync.argtypes = [vp]
+    lib.lbm_run_timed.argtypes = [vp, C.c_int, fp]
+    lib.lbm_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    lib.lbm_get_info.argtypes = [vp, C.POINTER(LbmInfo)]
+    lib.lbm_device_count.argtypes = []
+    lib.lbm_abi_version.argtypes = []
+    lib.lbm_last_error.argtypes = []
+    lib.lbm_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def partition_rows(ny: int, nparts: int, part: int):
+    """lbm_partition_rows in Python (kept in lock-step by tests/test_host_logic.py)."""
+    base, rem = divmod(ny, nparts)
+    rows = base + (1 if part < rem else 0)
+    y0 = part * base + min(part, rem)
+    return y0, rows
+
+
+def to_c_params(p: Params) -> LbmParams:
+    return LbmParams(p.density, p.accel, p.omega, p.free_cells_inv, p.nx, p.ny, p.maxIters, p.reynolds_dim)
+
+
+def combine_av_sums(hi: np.ndarray, lo: np.ndarray, free_cells_inv: float) -> np.ndarray:
+    """lbm_combine_av_sums in numpy: hi/lo are [nparts, n]; parts are added in index order
+    with an error-free TwoSum so the result does not depend on how rows were split."""
+    hi = np.asarray(hi, dtype=np.float64)
+    lo = np.asarray(lo, dtype=np.float64)
+    H = np.zeros(hi.shape[1], dtype=np.float64)
+    L = np.zeros(hi.shape[1], dtype=np.float64)
+    for part in range(hi.shape[0]):
+        x = hi[part]
+        s = H + x
+        bb = s - H
+        err = (H - (s - bb)) + (x - bb)
+        H = s
+        L = (L + lo[part]) + err
+    return ((H + L) * np.float64(np.float32(free_cells_inv))).astype(np.float32)
+
+
+class Simulation:
+    """One lbm_ctx.  Mirrors the reference host's use of its device state (d2q9-bgk.c:194-277):
+    create -> upload -> run -> sync -> download -> destroy."""
+
+    def __init__(self, params: Params, ngpus: int = 1, devices=None, slab=None, options=None):
+        """slab = (device, rank, nranks, y0, rows) creates the one-process-per-GPU form."""
+        self.lib = load_library()
+        self.params = params
+        self._cp = to_c_params(params)
+        self._ctx = C.c_void_p()
+        if slab is not None:
+            device, rank, nranks, y0, rows = slab
+            self._ck(self.lib.lbm_create_slab(C.byref(self._ctx), C.byref(self._cp), device, rank, nranks, y0, rows))
+            self.rows = rows
+        elif devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            self._ck(self.lib.lbm_create_on(C.byref(self._ctx), C.byref(self._cp), len(devices), arr))
+            self.rows = params.ny
+        else:
+            self._ck(self.lib.lbm_create(C.byref(self._ctx), C.byref(self._cp), ngpus))
+            self.rows = params.ny
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
+
+    def _ck(self, status: int):
+        if status != 0:
+            raise LbmError(self.lib.lbm_last_error().decode())
+
+    # -- options / info ------------------------------------------------------
+    def set_option(self, key: str, value: int):
+        self._ck(self.lib.lbm_set_option(self._ctx, key.encode(), int(value)))
+
+    def info(self) -> dict:
+        info = LbmInfo()
+        self._ck(self.lib.lbm_get_info(self._ctx, C.byref(info)))
+        d = {name: getattr(info, name) for name, _ in LbmInfo._fields_}
+        d["kernel_name"] = info.kernel_name.decode()
+        return d
+
+    # -- ring plumbing ---------------------------------------------------------
+    def export_blob(self) -> bytes:
+        buf = C.create_string_buffer(self.lib.lbm_export_size())
+        self._ck(self.lib.lbm_export(self._ctx, buf))
+        return buf.raw
+
+    def connect(self, blob_down: bytes, blob_up: bytes):
+        self._ck(self.lib.lbm_connect(self._ctx, C.c_char_p(blob_down), C.c_char_p(blob_up)))
+
+    def halo_push(self):
+        self._ck(self.lib.lbm_halo_push(self._ctx))
+
+    # -- data ------------------------------------------------------------------
+    @staticmethod
+    def _ptr(a):
+        """numpy array or torch tensor (CPU) -> void*"""
+        if hasattr(a, "data_ptr"):
+            return C.c_void_p(a.data_ptr())
+        return C.c_void_p(a.ctypes.data)
+
+    def upload(self, cells, obstacles):
+        """cells: [9, rows, nx] float32, obstacles: [rows, nx] int32 (numpy, or pinned torch CPU tensors)."""
+        n = self.rows * self.params.nx
+        if isinstance(cells, np.ndarray):
+            cells = np.ascontiguousarray(cells, dtype=np.float32)
+            obstacles = np.ascontiguousarray(obstacles, dtype=np.int32)
+            assert cells.size == NSPEEDS * n and obstacles.size == n
+        else:
+            assert cells.numel() == NSPEEDS * n and obstacles.numel() == n and cells.is_contiguous()
+        self._keep = (cells, obstacles)
+        self._ck(self.lib.lbm_upload(self._ctx, self._ptr(cells), self._ptr(obstacles)))
+
+    def run(self, nsteps: int):
+        self._ck(self.lib.lbm_run(self._ctx, nsteps))
+
+    def run_timed(self, nsteps: int) -> float:
+        ms = C.c_float(0.0)
+        self._ck(self.lib.lbm_run_timed(self._ctx, nsteps, C.byref(ms)))
+        return float(ms.value)
+
+    def sync(self):
+        self._ck(self.lib.lbm_sync(self._ctx))
+
+    def download_cells(self, out=None):
+        if out is None:
+            out = np.empty((NSPEEDS, self.rows, self.params.nx), dtype=np.float32)
+        self._ck(self.lib.lbm_download_cells(self._ctx, self._ptr(out)))
+        return out
+
+    def download_av_vels(self, n: int) -> np.ndarray:
+        av = np.empty(max(n, 1), dtype=np.float32)
+        self._ck(self.lib.lbm_download_av_vels(self._ctx, av.ctypes.data_as(C.POINTER(C.c_float)), n))
+        return av[:n]
+
+    def download_av_sums(self, n: int):
+        hi = np.empty(max(n, 1), dtype=np.float64)
+        lo = np.empty(max(n, 1), dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        self._ck(self.lib.lbm_download_av_sums(self._ctx, hi.ctypes.data_as(dp), lo.ctypes.data_as(dp), n))
+        return hi[:n], lo[:n]
+
+    def close(self):
+        if self._ctx:
+            self.lib.lbm_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,796 @@
+// lbm_cuda.cu — the C-ABI of include/lbm.h over the sm_100a kernels.
+//
+// Replaces the device half of the reference host program: t_ocl and its buffers
+// (d2q9-bgk.c:97-119, :687-710), the uploads (:200-209), the time loop's three
+// launchers (:221-238, :282-393), clFinish (:239), the downloads (:251-260) and
+// the releases (:729-741).  No OpenCL, no JIT: kernels are compiled ahead of time
+// for sm_100a and physics constants travel as kernel arguments at full precision
+// (the reference bakes 6-decimal -D constants into a run-time build, :643-645).
+#include "lbm.h"
+#include "lbm_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return 1;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail("CUDA error during '%s' on line %d: %s", #call, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+constexpr unsigned long long BLOB_MAGIC = 0x4c424d4232303031ULL;  // "LBMB2001"
+
+// Geometry of one slab's lattice arena, enough for a neighbour to address its
+// ghost rows and flags: [buffer 0 | buffer 1 | flags].
+struct ArenaLayout {
+  long long plane_stride;  // floats
+  long long buf_floats;    // 9 * plane_stride
+  long long flags_offset;  // bytes from arena base
+  int rows;
+  int pitch;
+};
+
+struct Blob {
+  unsigned long long magic;
+  cudaIpcMemHandle_t handle;
+  ArenaLayout layout;
+  int device;
+  int rank;
+};
+
+struct Neighbour {
+  float* arena = nullptr;  // peer-addressable base of the neighbour's arena
+  ArenaLayout layout{};
+  bool ipc = false;        // arena came from cudaIpcOpenMemHandle
+};
+
+struct Slab {
+  int device = 0;
+  int y0 = 0, rows = 0;    // global rows [y0, y0 + rows)
+  cudaStream_t stream = nullptr;
+  float* arena = nullptr;
+  ArenaLayout layout{};
+  uint32_t* mask = nullptr;
+  float* partials = nullptr;
+  double* av_hi = nullptr;
+  double* av_lo = nullptr;
+  long long av_capacity = 0;
+  Neighbour up, down;
+  unsigned long long step_launches = 0;  // step kernels launched on this slab (for edge_target)
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+
+  float* row0(int buf) const { return arena + (long long)buf * layout.buf_floats + layout.pitch; }
+  unsigned long long* flags() const {
+    return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(arena) + layout.flags_offset);
+  }
+};
+
+float* nb_ghost_below(const Neighbour& n, int buf) {  // its ghost row -1
+  return n.arena + (long long)buf * n.layout.buf_floats;
+}
+float* nb_ghost_above(const Neighbour& n, int buf) {  // its ghost row `rows`
+  return n.arena + (long long)buf * n.layout.buf_floats + (long long)(n.layout.rows + 1) * n.layout.pitch;
+}
+unsigned long long* nb_flags(const Neighbour& n) {
+  return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(n.arena) + n.layout.flags_offset);
+}
+
+}  // namespace
+
+struct lbm_ctx {
+  lbm_params p{};
+  std::vector<Slab> slabs;
+  std::vector<std::pair<int, cudaStream_t>> streams;  // one per distinct device
+  int rank = 0, nranks = 1;
+  int y0 = 0, rows = 0;        // rows held by this context
+  int pitch = 0, mask_pitch = 0;
+  bool ring = false;           // more than one slab in the whole ring -> flag protocol
+  bool connected = false;
+  bool uploaded = false;
+  int cur = 0;                 // buffer holding the current state
+  unsigned long long epoch = 0;
+  long long steps_done = 0;    // since creation
+  long long steps_since_upload = 0;
+  long long launches = 0;
+  // options
+  int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0;
+  // resolved
+  int V = 1, tpb = 256, streaming = 0, chunk_steps = 1, segs = 1;
+  long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
+  float w1 = 0.f, w2 = 0.f;
+};
+
+namespace {
+
+int set_device(const Slab& s) {
+  CK(cudaSetDevice(s.device));
+  return 0;
+}
+
+cudaStream_t stream_for(lbm_ctx* ctx, int device, int* err) {
+  *err = 0;
+  for (auto& ds : ctx->streams)
+    if (ds.first == device) return ds.second;
+  cudaStream_t st = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+    *err = fail("cannot create a stream on device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  ctx->streams.emplace_back(device, st);
+  return st;
+}
+
+int validate(const lbm_params* p) {
+  if (!p) return fail("params is NULL");
+  if (p->nx < 1 || p->ny < 2) return fail("grid %dx%d is too small (need nx >= 1, ny >= 2)", p->nx, p->ny);
+  return 0;
+}
+
+void resolve_options(lbm_ctx* ctx) {
+  const int nx = ctx->p.nx;
+  int V = ctx->opt_v;
+  if (V != 1 && V != 2 && V != 4) V = 4;
+  while (V > 1 && nx % V != 0) V >>= 1;
+  ctx->V = V;
+  int tpb = ctx->opt_tpb;
+  if (tpb != 128 && tpb != 256 && tpb != 512) tpb = 256;
+  ctx->tpb = tpb;
+  ctx->segs = (nx + 32 * V - 1) / (32 * V);
+  const double lattice_bytes = 2.0 * 9.0 * 4.0 * (double)ctx->pitch * (double)(ctx->rows + 2);
+  ctx->streaming = ctx->opt_streaming >= 0 ? (ctx->opt_streaming != 0) : (lattice_bytes > 96.0 * 1024 * 1024);
+  long long per_step = 0;
+  for (auto& s : ctx->slabs) per_step = std::max(per_step, (long long)s.rows * ctx->segs);
+  ctx->per_step = per_step;
+  long long chunk = ctx->opt_chunk > 0 ? ctx->opt_chunk : (64LL << 20) / (4 * std::max(1LL, per_step));
+  ctx->chunk_steps = (int)std::max(1LL, std::min(chunk, 4096LL));
+}
+
+int alloc_slab(lbm_ctx* ctx, Slab& s) {
+  if (set_device(s)) return 1;
+  const int pitch = ctx->pitch;
+  s.layout.pitch = pitch;
+  s.layout.rows = s.rows;
+  s.layout.plane_stride = (long long)(s.rows + 2) * pitch;
+  s.layout.buf_floats = 9 * s.layout.plane_stride;
+  s.layout.flags_offset = 2 * s.layout.buf_floats * (long long)sizeof(float);
+  const size_t arena_bytes = (size_t)s.layout.flags_offset + 256;
+  CK(cudaMalloc(&s.arena, arena_bytes));
+  CK(cudaMemset(s.arena, 0, arena_bytes));
+  CK(cudaMalloc(&s.mask, sizeof(uint32_t) * (size_t)ctx->mask_pitch * s.rows));
+  CK(cudaMemset(s.mask, 0, sizeof(uint32_t) * (size_t)ctx->mask_pitch * s.rows));
+  CK(cudaEventCreate(&s.ev_start));
+  CK(cudaEventCreate(&s.ev_stop));
+  return 0;
+}
+
+int ensure_av_capacity(lbm_ctx* ctx, long long need) {
+  for (auto& s : ctx->slabs) {
+    if (s.av_capacity >= need) continue;
+    if (set_device(s)) return 1;
+    long long cap = std::max(need, std::max<long long>(s.av_capacity * 2, 1024));
+    double *hi = nullptr, *lo = nullptr;
+    CK(cudaMalloc(&hi, sizeof(double) * cap));
+    CK(cudaMalloc(&lo, sizeof(double) * cap));
+    CK(cudaMemsetAsync(hi, 0, sizeof(double) * cap, s.stream));
+    CK(cudaMemsetAsync(lo, 0, sizeof(double) * cap, s.stream));
+    if (s.av_capacity > 0) {
+      CK(cudaMemcpyAsync(hi, s.av_hi, sizeof(double) * s.av_capacity, cudaMemcpyDeviceToDevice, s.stream));
+      CK(cudaMemcpyAsync(lo, s.av_lo, sizeof(double) * s.av_capacity, cudaMemcpyDeviceToDevice, s.stream));
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    if (s.av_hi) CK(cudaFree(s.av_hi));
+    if (s.av_lo) CK(cudaFree(s.av_lo));
+    s.av_hi = hi;
+    s.av_lo = lo;
+    s.av_capacity = cap;
+  }
+  return 0;
+}
+
+int ensure_partials(lbm_ctx* ctx) {
+  for (auto& s : ctx->slabs) {
+    if (s.partials) continue;
+    if (set_device(s)) return 1;
+    CK(cudaMalloc(&s.partials, sizeof(float) * (size_t)ctx->chunk_steps * (size_t)s.rows * (size_t)ctx->segs));
+  }
+  return 0;
+}
+
+// Neighbours inside one process: slab i's up neighbour is slab i+1; the ring's
+// ends are closed here when the context is the whole ring.
+int wire_local_neighbours(lbm_ctx* ctx) {
+  const int n = (int)ctx->slabs.size();
+  for (int i = 0; i < n; i++) {
+    Slab& s = ctx->slabs[i];
+    if (i + 1 < n || ctx->nranks == 1) {
+      const Slab& u = ctx->slabs[(i + 1) % n];
+      s.up.arena = u.arena;
+      s.up.layout = u.layout;
+    }
+    if (i > 0 || ctx->nranks == 1) {
+      const Slab& d = ctx->slabs[(i + n - 1) % n];
+      s.down.arena = d.arena;
+      s.down.layout = d.layout;
+    }
+  }
+  // peer access between distinct devices
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      const int a = ctx->slabs[i].device, b = ctx->slabs[j].device;
+      if (a == b) continue;
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, a, b));
+      if (!can) return fail("device %d cannot access device %d (no P2P)", a, b);
+      CK(cudaSetDevice(a));
+      cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail("cudaDeviceEnablePeerAccess(%d -> %d): %s", a, b, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+    }
+  ctx->connected = (ctx->nranks == 1);
+  return 0;
+}
+
+int create_common(lbm_ctx** out, const lbm_params* p, int nslabs, const int* devices, int rank, int nranks,
+                  int y0, int rows) {
+  if (!out) return fail("out is NULL");
+  *out = nullptr;
+  if (validate(p)) return 1;
+  if (nslabs < 1 || nslabs > rows) return fail("cannot split %d rows into %d slabs", rows, nslabs);
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return fail("no CUDA device is visible");
+  lbm_ctx* ctx = new lbm_ctx();
+  ctx->p = *p;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ctx->y0 = y0;
+  ctx->rows = rows;
+  ctx->pitch = (p->nx + 31) / 32 * 32;
+  ctx->mask_pitch = ctx->pitch / 32;
+  ctx->ring = (nslabs > 1) || (nranks > 1);
+  ctx->w1 = p->density * p->accel / 9.0f;   // kernels.cl:14
+  ctx->w2 = p->density * p->accel / 36.0f;  // kernels.cl:15
+  ctx->slabs.resize(nslabs);
+  for (int i = 0; i < nslabs; i++) {
+    Slab& s = ctx->slabs[i];
+    s.device = devices[i];
+    if (s.device < 0 || s.device >= ndev) {
+      fail("device ordinal %d out of range (have %d)", s.device, ndev);
+      lbm_destroy(ctx);
+      return 1;
+    }
+    int sy0, srows;
+    lbm_partition_rows(rows, nslabs, i, &sy0, &srows);
+    s.y0 = y0 + sy0;
+    s.rows = srows;
+    int err = 0;
+    s.stream = stream_for(ctx, s.device, &err);
+    if (err || alloc_slab(ctx, s)) { lbm_destroy(ctx); return 1; }
+  }
+  if (wire_local_neighbours(ctx)) { lbm_destroy(ctx); return 1; }
+  resolve_options(ctx);
+  *out = ctx;
+  return 0;
+}
+
+template <int V, bool STREAM, int TPB>
+void launch_step_t(const lbm::StepArgs& a, long long warps, cudaStream_t st) {
+  const long long blocks = (warps + TPB / 32 - 1) / (TPB / 32);
+  lbm::step_kernel<V, STREAM, TPB><<<(unsigned)blocks, TPB, 0, st>>>(a);
+}
+
+template <int V, bool STREAM>
+void launch_step_v(int tpb, const lbm::StepArgs& a, long long warps, cudaStream_t st) {
+  if (tpb == 128) launch_step_t<V, STREAM, 128>(a, warps, st);
+  else if (tpb == 512) launch_step_t<V, STREAM, 512>(a, warps, st);
+  else launch_step_t<V, STREAM, 256>(a, warps, st);
+}
+
+void launch_step(int V, int streaming, int tpb, const lbm::StepArgs& a, long long warps, cudaStream_t st) {
+  if (streaming) {
+    if (V == 4) launch_step_v<4, true>(tpb, a, warps, st);
+    else if (V == 2) launch_step_v<2, true>(tpb, a, warps, st);
+    else launch_step_v<1, true>(tpb, a, warps, st);
+  } else {
+    if (V == 4) launch_step_v<4, false>(tpb, a, warps, st);
+    else if (V == 2) launch_step_v<2, false>(tpb, a, warps, st);
+    else launch_step_v<1, false>(tpb, a, warps, st);
+  }
+}
+
+// local row of global row ny-2 in this slab, or -1
+int accel_row_of(const lbm_ctx* ctx, const Slab& s) {
+  const int g = ctx->p.ny - 2;
+  return (g >= s.y0 && g < s.y0 + s.rows) ? g - s.y0 : -1;
+}
+
+int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
+  if (!ctx) return fail("ctx is NULL");
+  if (nsteps < 0) return fail("nsteps must be >= 0");
+  if (!ctx->uploaded) return fail("lbm_run before lbm_upload");
+  if (ctx->nranks > 1 && !ctx->connected) return fail("lbm_run before lbm_connect on a %d-rank ring", ctx->nranks);
+  if (ms) *ms = 0.f;
+  if (nsteps == 0) return 0;
+  if (ensure_av_capacity(ctx, ctx->steps_since_upload + nsteps)) return 1;
+  if (ensure_partials(ctx)) return 1;
+
+  if (timed)
+    for (auto& s : ctx->slabs) {
+      if (set_device(s)) return 1;
+      CK(cudaEventRecord(s.ev_start, s.stream));
+    }
+
+  // epoch 1 of the run: step 0's accelerate_flow on the resident state
+  ctx->epoch++;
+  for (auto& s : ctx->slabs) {
+    if (set_device(s)) return 1;
+    lbm::AccelArgs a{};
+    a.cur = s.row0(ctx->cur);
+    a.plane_stride = s.layout.plane_stride;
+    a.pitch = ctx->pitch;
+    a.nx = ctx->p.nx;
+    a.rows = s.rows;
+    a.mask = s.mask;
+    a.mask_pitch = ctx->mask_pitch;
+    a.w1 = ctx->w1;
+    a.w2 = ctx->w2;
+    a.accel_row = accel_row_of(ctx, s);
+    a.up_ghost = nb_ghost_below(s.up, ctx->cur);
+    a.up_plane_stride = s.up.layout.plane_stride;
+    a.down_ghost = nb_ghost_above(s.down, ctx->cur);
+    a.down_plane_stride = s.down.layout.plane_stride;
+    if (ctx->ring) {
+      a.peer_up_flag = nb_flags(s.up) + 1;     // the up neighbour's flag_from_down
+      a.peer_down_flag = nb_flags(s.down) + 0; // the down neighbour's flag_from_up
+    }
+    a.epoch = ctx->epoch;
+    if (a.accel_row >= 0 || ctx->ring) {
+      lbm::accelerate_kernel<<<1, 1024, 0, s.stream>>>(a);
+      ctx->launches++;
+    }
+  }
+
+  int in_chunk = 0;
+  long long chunk_first = ctx->steps_since_upload;
+  for (int t = 0; t < nsteps; t++) {
+    ctx->epoch++;
+    const bool last = (t == nsteps - 1);
+    for (auto& s : ctx->slabs) {
+      if (set_device(s)) return 1;
+      lbm::StepArgs a{};
+      a.src = s.row0(ctx->cur);
+      a.dst = s.row0(ctx->cur ^ 1);
+      a.plane_stride = s.layout.plane_stride;
+      a.pitch = ctx->pitch;
+      a.nx = ctx->p.nx;
+      a.rows = s.rows;
+      a.segs = ctx->segs;
+      a.mask = s.mask;
+      a.mask_pitch = ctx->mask_pitch;
+      a.omega = ctx->p.omega;
+      a.w1 = ctx->w1;
+      a.w2 = ctx->w2;
+      a.accel_row = last ? -1 : accel_row_of(ctx, s);
+      a.up_ghost = nb_ghost_below(s.up, ctx->cur ^ 1);
+      a.up_plane_stride = s.up.layout.plane_stride;
+      a.down_ghost = nb_ghost_above(s.down, ctx->cur ^ 1);
+      a.down_plane_stride = s.down.layout.plane_stride;
+      a.partials = s.partials + (long long)in_chunk * s.rows * ctx->segs;
+      if (ctx->ring) {
+        unsigned long long* f = s.flags();
+        a.flag_from_up = f + 0;
+        a.flag_from_down = f + 1;
+        a.edge_count = f + 2;
+        a.peer_up_flag = nb_flags(s.up) + 1;
+        a.peer_down_flag = nb_flags(s.down) + 0;
+        s.step_launches++;
+        a.edge_target = s.step_launches * (unsigned long long)ctx->segs;
+      }
+      a.epoch = ctx->epoch;
+      launch_step(ctx->V, ctx->streaming, ctx->tpb, a, (long long)s.rows * ctx->segs, s.stream);
+      ctx->launches++;
+    }
+    ctx->cur ^= 1;
+    in_chunk++;
+    if (in_chunk == ctx->chunk_steps || last) {
+      for (auto& s : ctx->slabs) {
+        if (set_device(s)) return 1;
+        lbm::av_finalize_kernel<<<in_chunk, 256, 0, s.stream>>>(s.partials, (long long)s.rows * ctx->segs, s.av_hi,
+                                                                  s.av_lo, chunk_first);
+        ctx->launches++;
+      }
+      chunk_first += in_chunk;
+      in_chunk = 0;
+    }
+  }
+  CK(cudaGetLastError());
+  ctx->steps_done += nsteps;
+  ctx->steps_since_upload += nsteps;
+
+  if (timed) {
+    float worst = 0.f;
+    for (auto& s : ctx->slabs) {
+      if (set_device(s)) return 1;
+      CK(cudaEventRecord(s.ev_stop, s.stream));
+    }
+    for (auto& s : ctx->slabs) {
+      if (set_device(s)) return 1;
+      CK(cudaEventSynchronize(s.ev_stop));
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, s.ev_start, s.ev_stop));
+      worst = std::max(worst, t);
+    }
+    if (ms) *ms = worst;
+  }
+  return 0;
+}
+
+int sync_all(lbm_ctx* ctx) {
+  for (auto& ds : ctx->streams) {
+    CK(cudaSetDevice(ds.first));
+    CK(cudaStreamSynchronize(ds.second));
+  }
+  return 0;
+}
+
+int push_halos(lbm_ctx* ctx) {
+  // Every slab copies its top row (all nine planes) into the up neighbour's ghost
+  // row below, and its bottom row into the down neighbour's ghost row above.
+  const size_t width = sizeof(float) * (size_t)ctx->p.nx;
+  for (auto& s : ctx->slabs) {
+    if (set_device(s)) return 1;
+    const float* top = s.row0(ctx->cur) + (long long)(s.rows - 1) * ctx->pitch;
+    const float* bot = s.row0(ctx->cur);
+    CK(cudaMemcpy2DAsync(nb_ghost_below(s.up, ctx->cur), sizeof(float) * s.up.layout.plane_stride, top,
+                         sizeof(float) * s.layout.plane_stride, width, 9, cudaMemcpyDefault, s.stream));
+    CK(cudaMemcpy2DAsync(nb_ghost_above(s.down, ctx->cur), sizeof(float) * s.down.layout.plane_stride, bot,
+                         sizeof(float) * s.layout.plane_stride, width, 9, cudaMemcpyDefault, s.stream));
+  }
+  return sync_all(ctx);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// exported functions
+// ---------------------------------------------------------------------------
+
+extern "C" {
+
+const char* lbm_last_error(void) { return g_error.c_str(); }
+int lbm_abi_version(void) { return LBM_ABI_VERSION; }
+
+int lbm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void lbm_partition_rows(int ny, int nparts, int part, int* y0, int* rows) {
+  const int base = ny / nparts, rem = ny % nparts;
+  const int r = base + (part < rem ? 1 : 0);
+  const int start = part * base + (part < rem ? part : rem);
+  if (y0) *y0 = start;
+  if (rows) *rows = r;
+}
+
+int lbm_create_on(lbm_ctx** out, const lbm_params* p, int nslabs, const int* devices) {
+  if (!devices) return fail("devices is NULL");
+  if (validate(p)) return 1;
+  return create_common(out, p, nslabs, devices, 0, 1, 0, p->ny);
+}
+
+int lbm_create(lbm_ctx** out, const lbm_params* p, int ngpus) {
+  if (validate(p)) return 1;
+  std::vector<int> devices;
+  if (const char* env = getenv("LBM_DEVICES")) {
+    for (const char* c = env; *c;) {
+      char* end = nullptr;
+      long v = strtol(c, &end, 10);
+      if (end == c) break;
+      devices.push_back((int)v);
+      c = (*end == ',') ? end + 1 : end;
+    }
+  }
+  if (ngpus <= 0) {
+    const char* env = getenv("LBM_NGPUS");
+    ngpus = env ? atoi(env) : (devices.empty() ? 1 : (int)devices.size());
+    if (ngpus <= 0) ngpus = 1;
+  }
+  if (devices.empty())
+    for (int i = 0; i < ngpus; i++) devices.push_back(i);
+  if ((int)devices.size() < ngpus) return fail("LBM_DEVICES lists %zu devices, %d needed", devices.size(), ngpus);
+  return create_common(out, p, ngpus, devices.data(), 0, 1, 0, p->ny);
+}
+
+int lbm_create_slab(lbm_ctx** out, const lbm_params* p, int device, int rank, int nranks, int y0, int rows) {
+  if (validate(p)) return 1;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
+  if (rows < 1 || y0 < 0 || y0 + rows > p->ny) return fail("bad row range [%d, %d) of %d", y0, y0 + rows, p->ny);
+  return create_common(out, p, 1, &device, rank, nranks, y0, rows);
+}
+
+size_t lbm_export_size(void) { return sizeof(Blob); }
+
+int lbm_export(lbm_ctx* ctx, void* blob) {
+  if (!ctx || !blob) return fail("lbm_export: NULL argument");
+  if (ctx->slabs.size() != 1) return fail("lbm_export needs a one-slab context (lbm_create_slab)");
+  Slab& s = ctx->slabs[0];
+  if (set_device(s)) return 1;
+  Blob b{};
+  b.magic = BLOB_MAGIC;
+  CK(cudaIpcGetMemHandle(&b.handle, s.arena));
+  b.layout = s.layout;
+  b.device = s.device;
+  b.rank = ctx->rank;
+  memcpy(blob, &b, sizeof b);
+  return 0;
+}
+
+int lbm_connect(lbm_ctx* ctx, const void* blob_down, const void* blob_up) {
+  if (!ctx || !blob_down || !blob_up) return fail("lbm_connect: NULL argument");
+  if (ctx->slabs.size() != 1) return fail("lbm_connect needs a one-slab context (lbm_create_slab)");
+  if (ctx->nranks == 1) return 0;
+  Slab& s = ctx->slabs[0];
+  if (set_device(s)) return 1;
+  Blob d, u;
+  memcpy(&d, blob_down, sizeof d);
+  memcpy(&u, blob_up, sizeof u);
+  if (d.magic != BLOB_MAGIC || u.magic != BLOB_MAGIC) return fail("lbm_connect: not an lbm_export blob");
+  if (d.layout.pitch != ctx->pitch || u.layout.pitch != ctx->pitch) return fail("lbm_connect: neighbour pitch differs");
+  void* pd = nullptr;
+  CK(cudaIpcOpenMemHandle(&pd, d.handle, cudaIpcMemLazyEnablePeerAccess));
+  s.down.arena = static_cast<float*>(pd);
+  s.down.layout = d.layout;
+  s.down.ipc = true;
+  if (memcmp(&d.handle, &u.handle, sizeof d.handle) == 0) {  // two-rank ring: one neighbour, both sides
+    s.up.arena = s.down.arena;
+    s.up.layout = d.layout;
+    s.up.ipc = false;
+  } else {
+    void* pu = nullptr;
+    CK(cudaIpcOpenMemHandle(&pu, u.handle, cudaIpcMemLazyEnablePeerAccess));
+    s.up.arena = static_cast<float*>(pu);
+    s.up.layout = u.layout;
+    s.up.ipc = true;
+  }
+  ctx->connected = true;
+  return 0;
+}
+
+void lbm_destroy(lbm_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& ds : ctx->streams) {
+    cudaSetDevice(ds.first);
+    cudaStreamSynchronize(ds.second);
+  }
+  for (auto& s : ctx->slabs) {
+    cudaSetDevice(s.device);
+    if (s.up.ipc && s.up.arena) cudaIpcCloseMemHandle(s.up.arena);
+    if (s.down.ipc && s.down.arena) cudaIpcCloseMemHandle(s.down.arena);
+    if (s.arena) cudaFree(s.arena);
+    if (s.mask) cudaFree(s.mask);
+    if (s.partials) cudaFree(s.partials);
+    if (s.av_hi) cudaFree(s.av_hi);
+    if (s.av_lo) cudaFree(s.av_lo);
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_stop) cudaEventDestroy(s.ev_stop);
+  }
+  for (auto& ds : ctx->streams) {
+    cudaSetDevice(ds.first);
+    cudaStreamDestroy(ds.second);
+  }
+  (void)cudaGetLastError();
+  delete ctx;
+}
+
+int lbm_upload(lbm_ctx* ctx, const float* cells_soa, const int* obstacles) {
+  if (!ctx || !cells_soa || !obstacles) return fail("lbm_upload: NULL argument");
+  if (sync_all(ctx)) return 1;
+  resolve_options(ctx);
+  for (auto& s : ctx->slabs)
+    if (s.partials) {  // geometry options may have changed
+      if (set_device(s)) return 1;
+      CK(cudaFree(s.partials));
+      s.partials = nullptr;
+    }
+  const int nx = ctx->p.nx;
+  const size_t host_plane = (size_t)nx * ctx->rows;
+  ctx->cur = 0;
+  for (auto& s : ctx->slabs) {
+    if (set_device(s)) return 1;
+    const size_t row_off = (size_t)(s.y0 - ctx->y0) * nx;
+    for (int k = 0; k < 9; k++)
+      CK(cudaMemcpy2DAsync(s.row0(0) + k * s.layout.plane_stride, sizeof(float) * ctx->pitch,
+                           cells_soa + k * host_plane + row_off, sizeof(float) * nx, sizeof(float) * nx, s.rows,
+                           cudaMemcpyHostToDevice, s.stream));
+    // obstacle ints -> bit mask, staged through a bounded device buffer
+    const int stage_rows = (int)std::max<long long>(1, std::min<long long>(s.rows, (64LL << 20) / std::max(1, nx)));
+    int* stage = nullptr;
+    CK(cudaMalloc(&stage, sizeof(int) * (size_t)stage_rows * nx));
+    for (int r0 = 0; r0 < s.rows; r0 += stage_rows) {
+      const int nr = std::min(stage_rows, s.rows - r0);
+      CK(cudaMemcpyAsync(stage, obstacles + row_off + (size_t)r0 * nx, sizeof(int) * (size_t)nr * nx,
+                         cudaMemcpyHostToDevice, s.stream));
+      dim3 grid(ctx->mask_pitch, nr);
+      lbm::pack_obstacles_kernel<<<grid, 32, 0, s.stream>>>(stage, nx, s.mask + (size_t)r0 * ctx->mask_pitch,
+                                                            ctx->mask_pitch);
+      ctx->launches++;
+      CK(cudaStreamSynchronize(s.stream));  // `stage` and pageable host memory are reused
+    }
+    CK(cudaFree(stage));
+    if (s.av_hi) CK(cudaMemsetAsync(s.av_hi, 0, sizeof(double) * s.av_capacity, s.stream));
+    if (s.av_lo) CK(cudaMemsetAsync(s.av_lo, 0, sizeof(double) * s.av_capacity, s.stream));
+  }
+  CK(cudaGetLastError());
+  if (sync_all(ctx)) return 1;
+  ctx->steps_since_upload = 0;
+  ctx->uploaded = true;
+  if (ctx->nranks == 1) return push_halos(ctx);
+  return 0;
+}
+
+int lbm_halo_push(lbm_ctx* ctx) {
+  if (!ctx) return fail("ctx is NULL");
+  if (!ctx->uploaded) return fail("lbm_halo_push before lbm_upload");
+  if (ctx->nranks > 1 && !ctx->connected) return fail("lbm_halo_push before lbm_connect");
+  return push_halos(ctx);
+}
+
+int lbm_download_cells(lbm_ctx* ctx, float* cells_soa) {
+  if (!ctx || !cells_soa) return fail("lbm_download_cells: NULL argument");
+  if (!ctx->uploaded) return fail("lbm_download_cells before lbm_upload");
+  const int nx = ctx->p.nx;
+  const size_t host_plane = (size_t)nx * ctx->rows;
+  for (auto& s : ctx->slabs) {
+    if (set_device(s)) return 1;
+    const size_t row_off = (size_t)(s.y0 - ctx->y0) * nx;
+    for (int k = 0; k < 9; k++)
+      CK(cudaMemcpy2DAsync(cells_soa + k * host_plane + row_off, sizeof(float) * nx,
+                           s.row0(ctx->cur) + k * s.layout.plane_stride, sizeof(float) * ctx->pitch,
+                           sizeof(float) * nx, s.rows, cudaMemcpyDeviceToHost, s.stream));
+  }
+  return sync_all(ctx);
+}
+
+int lbm_download_av_sums(lbm_ctx* ctx, double* hi, double* lo, int n) {
+  if (!ctx || !hi || !lo) return fail("lbm_download_av_sums: NULL argument");
+  if (n < 0 || n > ctx->steps_since_upload) return fail("asked for %d averages, %lld steps run", n, ctx->steps_since_upload);
+  if (ctx->slabs.size() != 1) return fail("lbm_download_av_sums needs a one-slab context");
+  Slab& s = ctx->slabs[0];
+  if (set_device(s)) return 1;
+  if (n == 0) return 0;
+  CK(cudaMemcpyAsync(hi, s.av_hi, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaMemcpyAsync(lo, s.av_lo, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+void lbm_combine_av_sums(const double* hi, const double* lo, int nparts, int n, int stride, float free_cells_inv,
+                         float* av) {
+  for (int i = 0; i < n; i++) {
+    double H = 0.0, L = 0.0;
+    for (int part = 0; part < nparts; part++) {  // fixed part order; TwoSum keeps the rounding error
+      const double x = hi[(size_t)part * stride + i];
+      volatile double s = H + x;
+      volatile double bb = s - H;
+      volatile double err = (H - (s - bb)) + (x - bb);
+      H = s;
+      L = (L + lo[(size_t)part * stride + i]) + err;
+    }
+    av[i] = (float)((H + L) * (double)free_cells_inv);  // kernels.cl:202 scales by FREE_CELLS_INV
+  }
+}
+
+int lbm_download_av_vels(lbm_ctx* ctx, float* av, int n) {
+  if (!ctx || !av) return fail("lbm_download_av_vels: NULL argument");
+  if (ctx->nranks != 1) return fail("lbm_download_av_vels on a multi-process ring: use lbm_download_av_sums");
+  if (n < 0 || n > ctx->steps_since_upload) return fail("asked for %d averages, %lld steps run", n, ctx->steps_since_upload);
+  if (n == 0) return 0;
+  const int parts = (int)ctx->slabs.size();
+  std::vector<double> hi((size_t)parts * n), lo((size_t)parts * n);
+  for (int i = 0; i < parts; i++) {
+    Slab& s = ctx->slabs[i];
+    if (set_device(s)) return 1;
+    CK(cudaMemcpyAsync(hi.data() + (size_t)i * n, s.av_hi, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(lo.data() + (size_t)i * n, s.av_lo, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
+  }
+  if (sync_all(ctx)) return 1;
+  lbm_combine_av_sums(hi.data(), lo.data(), parts, n, n, ctx->p.free_cells_inv, av);
+  return 0;
+}
+
+void* lbm_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    (void)cudaGetLastError();
+    fail("cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void lbm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int lbm_run(lbm_ctx* ctx, int nsteps) { return run_impl(ctx, nsteps, false, nullptr); }
+
+int lbm_run_timed(lbm_ctx* ctx, int nsteps, float* ms) { return run_impl(ctx, nsteps, true, ms); }
+
+int lbm_sync(lbm_ctx* ctx) {
+  if (!ctx) return fail("ctx is NULL");
+  return sync_all(ctx);
+}
+
+int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
+  if (!ctx || !key) return fail("lbm_set_option: NULL argument");
+  if (!strcmp(key, "cells_per_thread")) ctx->opt_v = (int)value;
+  else if (!strcmp(key, "threads_per_block")) ctx->opt_tpb = (int)value;
+  else if (!strcmp(key, "streaming")) ctx->opt_streaming = (int)value;
+  else if (!strcmp(key, "persistent")) ctx->opt_persistent = (int)value;
+  else if (!strcmp(key, "chunk_steps")) ctx->opt_chunk = (int)value;
+  else return fail("unknown option '%s'", key);
+  if (sync_all(ctx)) return 1;
+  const int old_chunk = ctx->chunk_steps;
+  const long long old_per_step = ctx->per_step;
+  resolve_options(ctx);
+  if (ctx->chunk_steps != old_chunk || ctx->per_step != old_per_step)
+    for (auto& s : ctx->slabs)
+      if (s.partials) {
+        if (set_device(s)) return 1;
+        CK(cudaFree(s.partials));
+        s.partials = nullptr;
+      }
+  return 0;
+}
+
+int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
+  if (!ctx || !info) return fail("lbm_get_info: NULL argument");
+  memset(info, 0, sizeof *info);
+  info->abi_version = LBM_ABI_VERSION;
+  info->nslabs = (int)ctx->slabs.size();
+  info->rank = ctx->rank;
+  info->nranks = ctx->nranks;
+  info->y0 = ctx->y0;
+  info->rows = ctx->rows;
+  info->pitch = ctx->pitch;
+  info->cells_per_thread = ctx->V;
+  info->threads_per_block = ctx->tpb;
+  info->streaming = ctx->streaming;
+  info->steps_per_launch = 1;
+  info->steps_done = ctx->steps_done;
+  info->kernel_launches = ctx->launches;
+  info->partials_per_step = ctx->per_step;
+  snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,stream=%d,tpb=%d>", ctx->V,
+           ctx->streaming, ctx->tpb);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: long CPU oracle runs, not part of the default CPU suite")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle_lib
+    oracle_lib.load("base")
+    return oracle_lib
+
+
+@pytest.fixture(scope="session")
+def lbm():
+    """The product package; the CUDA library must already be built (make / build())."""
+    import opencl_lattice_boltzmann_b200 as pkg
+    pkg.cabi.load_library()
+    return pkg

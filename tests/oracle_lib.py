@@ -1,0 +1,151 @@
+"""ctypes loader for oracle/liboracle.so — the CHECKER, used by tests/, smoke() and bench.py's
+cpu_baseline / reference-arm legs only (never by the product path)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+class OracleParams(C.Structure):
+    _fields_ = [("density", C.c_float), ("accel", C.c_float), ("omega", C.c_float),
+                ("free_cells_inv", C.c_float), ("nx", C.c_int), ("ny", C.c_int),
+                ("maxIters", C.c_int), ("reynolds_dim", C.c_int)]
+
+
+class OracleParams64(C.Structure):
+    _fields_ = [("density", C.c_double), ("accel", C.c_double), ("omega", C.c_double),
+                ("nx", C.c_int), ("ny", C.c_int), ("maxIters", C.c_int), ("reynolds_dim", C.c_int)]
+
+
+def build_oracle() -> None:
+    subprocess.run(["make", "-C", ORACLE_DIR, "--no-print-directory"], check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+def _cpu_has_avx2() -> bool:
+    try:
+        with open("/proc/cpuinfo") as fp:
+            return " avx2 " in fp.read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+_lib_cache = {}
+
+
+def load(variant: str = "base"):
+    """variant: 'base' (-O3 -fopenmp, the north-star baseline flags), 'avx2', or 'fastest'."""
+    if variant == "fastest":
+        variant = "avx2" if _cpu_has_avx2() else "base"
+    if variant in _lib_cache:
+        return _lib_cache[variant]
+    name = {"base": "liboracle.so", "avx2": "liboracle_avx2.so"}[variant]
+    path = os.path.join(ORACLE_DIR, name)
+    if not os.path.exists(path):
+        build_oracle()
+    lib = C.CDLL(path)
+    fp, ip, dp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)
+    P, P64 = C.POINTER(OracleParams), C.POINTER(OracleParams64)
+    lib.oracle_f32_accelerate.argtypes = [P, fp, ip]
+    lib.oracle_f32_accelerate.restype = None
+    lib.oracle_f32_timestep.argtypes = [P, fp, fp, ip, C.c_int]
+    lib.oracle_f32_timestep.restype = C.c_float
+    lib.oracle_f32_run.argtypes = [P, fp, fp, ip, C.c_int, fp, C.c_int]
+    lib.oracle_f32_run.restype = None
+    lib.oracle_f32_av_velocity.argtypes = [P, fp, ip]
+    lib.oracle_f32_av_velocity.restype = C.c_float
+    lib.oracle_f32_reynolds.argtypes = [P, fp, ip]
+    lib.oracle_f32_reynolds.restype = C.c_float
+    lib.oracle_f32_total_density.argtypes = [P, fp]
+    lib.oracle_f32_total_density.restype = C.c_float
+    lib.oracle_f32_final_state.argtypes = [P, fp, ip, fp, fp, fp, fp]
+    lib.oracle_f32_final_state.restype = None
+    lib.oracle_f32_slab_accelerate.argtypes = [P, fp, ip, C.c_int, C.c_int]
+    lib.oracle_f32_slab_accelerate.restype = None
+    lib.oracle_f32_slab_timestep.argtypes = [P, fp, fp, ip, C.c_int, fp]
+    lib.oracle_f32_slab_timestep.restype = None
+    lib.oracle_f64_run.argtypes = [P64, dp, dp, ip, C.c_int, dp]
+    lib.oracle_f64_run.restype = None
+    lib.oracle_f64_av_velocity.argtypes = [P64, dp, ip]
+    lib.oracle_f64_av_velocity.restype = C.c_double
+    lib.oracle_f64_pressure.argtypes = [P64, dp, ip, dp]
+    lib.oracle_f64_pressure.restype = None
+    lib.oracle_num_threads.argtypes = []
+    lib.oracle_num_threads.restype = C.c_int
+    _lib_cache[variant] = lib
+    return lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def to_oracle_params(params) -> OracleParams:
+    return OracleParams(params.density, params.accel, params.omega, params.free_cells_inv,
+                        params.nx, params.ny, params.maxIters, params.reynolds_dim)
+
+
+def run_f32(params, cells, obstacles, nsteps, reference_order=True, variant="base"):
+    """Runs nsteps of the fp32 oracle; returns (final cells [9,ny,nx], av_vels[nsteps])."""
+    lib = load(variant)
+    op = to_oracle_params(params)
+    cells = np.ascontiguousarray(cells, dtype=np.float32).copy()
+    scratch = np.empty_like(cells)
+    obstacles = np.ascontiguousarray(obstacles, dtype=np.int32)
+    av = np.zeros(max(nsteps, 1), dtype=np.float32)
+    lib.oracle_f32_run(C.byref(op), _fp(cells), _fp(scratch), _ip(obstacles), nsteps, _fp(av),
+                       1 if reference_order else 0)
+    return cells, av[:nsteps]
+
+
+def run_f64(params, cells, obstacles, nsteps):
+    """Runs nsteps of the fp64 oracle from fp64-exact deck constants; returns (cells, av_vels, pressure)."""
+    lib = load("base")
+    op = OracleParams64(params.density, params.accel, params.omega, params.nx, params.ny,
+                        params.maxIters, params.reynolds_dim)
+    cells = np.ascontiguousarray(cells, dtype=np.float64).copy()
+    scratch = np.empty_like(cells)
+    obstacles = np.ascontiguousarray(obstacles, dtype=np.int32)
+    av = np.zeros(max(nsteps, 1), dtype=np.float64)
+    lib.oracle_f64_run(C.byref(op), _dp(cells), _dp(scratch), _ip(obstacles), nsteps, _dp(av))
+    pressure = np.empty((params.ny, params.nx), dtype=np.float64)
+    lib.oracle_f64_pressure(C.byref(op), _dp(cells), _ip(obstacles), _dp(pressure))
+    return cells, av[:nsteps], pressure
+
+
+def final_state_f32(params, cells, obstacles):
+    lib = load("base")
+    op = to_oracle_params(params)
+    cells = np.ascontiguousarray(cells, dtype=np.float32)
+    obstacles = np.ascontiguousarray(obstacles, dtype=np.int32)
+    outs = [np.empty((params.ny, params.nx), dtype=np.float32) for _ in range(4)]
+    lib.oracle_f32_final_state(C.byref(op), _fp(cells), _ip(obstacles), *[_fp(o) for o in outs])
+    return outs
+
+
+def av_velocity_f32(params, cells, obstacles) -> float:
+    lib = load("base")
+    op = to_oracle_params(params)
+    return float(lib.oracle_f32_av_velocity(C.byref(op), _fp(np.ascontiguousarray(cells, dtype=np.float32)),
+                                            _ip(np.ascontiguousarray(obstacles, dtype=np.int32))))
+
+
+def reynolds_f32(params, cells, obstacles) -> float:
+    lib = load("base")
+    op = to_oracle_params(params)
+    return float(lib.oracle_f32_reynolds(C.byref(op), _fp(np.ascontiguousarray(cells, dtype=np.float32)),
+                                         _ip(np.ascontiguousarray(obstacles, dtype=np.int32))))

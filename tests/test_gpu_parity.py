@@ -1,0 +1,138 @@
+"""GPU parity: the CUDA path through the C-ABI against the CPU oracle (bit-exact lattice) and the
+reference's goldens (check.py's 1 % gate).  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import bits, pct_diff, random_case
+
+pytestmark = pytest.mark.gpu
+
+# av_vels: the GPU sums speeds exactly (double-double) and scales once; the reference scales each
+# work-item by FREE_CELLS_INV and adds in a fp32 tree (kernels.cl:202-229) — a few fp32 ulps apart.
+AV_RTOL = 2e-6
+
+SHAPES = [(128, 128), (256, 64), (100, 37), (34, 9), (33, 5), (8, 3), (1024, 16), (4096, 8), (4, 2), (1, 4)]
+
+
+def run_gpu(lbm, p, cells, obstacles, nsteps, **kw):
+    with lbm.cabi.Simulation(p, **kw) as sim:
+        sim.upload(cells, obstacles)
+        sim.run(nsteps)
+        sim.sync()
+        return sim.download_cells(), sim.download_av_vels(nsteps), sim.info()
+
+
+@pytest.mark.parametrize("nx,ny", SHAPES)
+def test_lattice_bit_exact_vs_oracle(lbm, oracle, nx, ny):
+    p, cells, obstacles = random_case(nx, ny, seed=nx * 1000 + ny)
+    nsteps = 7
+    ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, nsteps)
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, nsteps)
+    assert np.array_equal(bits(got_cells), bits(ref_cells)), info
+    np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("V", [1, 2, 4])
+@pytest.mark.parametrize("tpb", [128, 256, 512])
+@pytest.mark.parametrize("streaming", [0, 1])
+def test_kernel_variants_bit_exact(lbm, oracle, V, tpb, streaming):
+    p, cells, obstacles = random_case(384, 24, seed=7, walls=False)  # open edges: y wrap carries fluid
+    ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 5)
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 5,
+                                      options={"cells_per_thread": V, "threads_per_block": tpb, "streaming": streaming})
+    assert info["cells_per_thread"] == V and info["threads_per_block"] == tpb and info["streaming"] == streaming
+    assert np.array_equal(bits(got_cells), bits(ref_cells))
+    np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
+
+
+def test_split_runs_equal_one_run(lbm):
+    """accelerate is applied on the write side for the next step and skipped on the last step of a
+    run: run(5)+run(6) must be run(11) bit for bit, and an odd count reads the right buffer."""
+    p, cells, obstacles = random_case(256, 32, seed=3)
+    a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 11)
+    with lbm.cabi.Simulation(p) as sim:
+        sim.upload(cells, obstacles)
+        sim.run(5)
+        sim.run(6)
+        sim.sync()
+        b_cells, b_av = sim.download_cells(), sim.download_av_vels(11)
+    assert np.array_equal(bits(a_cells), bits(b_cells))
+    assert np.array_equal(bits(a_av), bits(b_av))
+
+
+@pytest.mark.parametrize("nslabs", [2, 3, 5])
+def test_row_slabs_on_one_gpu_equal_single(lbm, nslabs):
+    """The multi-slab path (ghost rows, edge stores into the neighbour, epoch flags) on ONE device:
+    lattice and av_vels bitwise equal to the single-slab run."""
+    p, cells, obstacles = random_case(256, 41, seed=11, walls=False)
+    a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 9)
+    b_cells, b_av, info = run_gpu(lbm, p, cells, obstacles, 9, devices=[0] * nslabs)
+    assert info["nslabs"] == nslabs
+    assert np.array_equal(bits(a_cells), bits(b_cells))
+    assert np.array_equal(bits(a_av), bits(b_av))
+
+
+def test_chunked_av_vels(lbm):
+    p, cells, obstacles = random_case(128, 16, seed=5)
+    _, a_av, _ = run_gpu(lbm, p, cells, obstacles, 23)
+    _, b_av, _ = run_gpu(lbm, p, cells, obstacles, 23, options={"chunk_steps": 4})
+    assert np.array_equal(bits(a_av), bits(b_av))
+
+
+def test_mass_conserved(lbm):
+    """total_density (d2q9-bgk.c:754-770) is invariant: collision conserves mass, rebound permutes,
+    accelerate moves mass between links of a cell."""
+    p, cells, obstacles = random_case(512, 64, seed=9)
+    got, _, _ = run_gpu(lbm, p, cells, obstacles, 50)
+    before = cells.astype(np.float64).sum()
+    after = got.astype(np.float64).sum()
+    assert abs(after - before) / before < 1e-6
+
+
+@pytest.mark.parametrize("name", ["128x128", "128x256", "256x256", "1024x1024"])
+def test_reference_decks_pass_checker(lbm, name):
+    """The four reference decks at full length against the reference's goldens with check.py's measure
+    (1 % on av_vels and on final-state pressure; check/check.py:84-135)."""
+    p, cells, obstacles = lbm.decks.load_deck(*lbm.decks.deck_paths(name))
+    got_cells, got_av, _ = run_gpu(lbm, p, cells, obstacles, p.maxIters)
+    worst_av, step = pct_diff(helpers.golden_av_vels(name), got_av)
+    assert np.isfinite(worst_av) and abs(worst_av) < 1.0, (worst_av, step)
+    ref_pressure = helpers.golden_pressure(name)
+    if ref_pressure is not None:
+        _, _, _, pressure = lbm.decks.final_state_fields(p, got_cells, obstacles)
+        worst_p, where = pct_diff(ref_pressure, pressure.ravel())
+        assert np.isfinite(worst_p) and abs(worst_p) < 1.0, (worst_p, where)
+
+
+def test_reynolds_known_answer(lbm):
+    """README.md:78 of the reference: Reynolds number 9.763598020526E+00 for 128x128 (fp64 serial);
+    the fp32 path must land within the checker's 1 %."""
+    p, cells, obstacles = lbm.decks.load_deck(*lbm.decks.deck_paths("128x128"))
+    got_cells, got_av, _ = run_gpu(lbm, p, cells, obstacles, p.maxIters)
+    re = lbm.decks.calc_reynolds(p, float(got_av[-1]))
+    assert abs(re - 9.763598020526) / 9.763598020526 < 0.01
+
+
+def test_full_row_length_slab_vs_oracle(lbm, oracle):
+    """BASELINE's row length (nx = 16384) on a slab the oracle finishes in seconds."""
+    p, cells, obstacles = lbm.decks.synthetic_channel(16384, 256, block=16, spacing=128)
+    rng = np.random.default_rng(1)
+    cells = (cells * (1.0 + 0.1 * (rng.random(cells.shape, dtype=np.float32) - 0.5))).astype(np.float32)
+    ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 3, reference_order=False)
+    got_cells, got_av, _ = run_gpu(lbm, p, cells, obstacles, 3, options={"streaming": 1})
+    assert np.array_equal(bits(got_cells), bits(ref_cells))
+    np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
+
+
+def test_errors_are_loud(lbm):
+    p, cells, obstacles = random_case(64, 8)
+    with lbm.cabi.Simulation(p) as sim:
+        with pytest.raises(lbm.cabi.LbmError, match="before lbm_upload"):
+            sim.run(1)
+        with pytest.raises(lbm.cabi.LbmError, match="unknown option"):
+            sim.set_option("nonsense", 1)
+        sim.upload(cells, obstacles)
+        sim.run(2)
+        with pytest.raises(lbm.cabi.LbmError, match="asked for"):
+            sim.download_av_vels(3)

@@ -1,0 +1,51 @@
+"""Kernel-variant sweep on one GPU (development tool; not the bench).  Prints MLUPS and the
+fraction of the measured HBM copy bandwidth for each (cells_per_thread, threads_per_block, streaming)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import opencl_lattice_boltzmann_b200 as lbm  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nx", type=int, default=16384)
+    ap.add_argument("--ny", type=int, default=16384)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--variants", default="4:256:1,4:128:1,4:512:1,2:256:1,2:128:1,1:256:1,4:256:0")
+    args = ap.parse_args()
+    peak = 6546.2
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    t0 = time.time()
+    p, cells, obstacles = lbm.decks.synthetic_channel(args.nx, args.ny)
+    print(f"deck built in {time.time()-t0:.1f}s", flush=True)
+    sim = lbm.cabi.Simulation(p)
+    t0 = time.time()
+    sim.upload(cells, obstacles)
+    print(f"upload {time.time()-t0:.2f}s", flush=True)
+    for var in args.variants.split(","):
+        V, tpb, st = (int(x) for x in var.split(":"))
+        sim.set_option("cells_per_thread", V)
+        sim.set_option("threads_per_block", tpb)
+        sim.set_option("streaming", st)
+        sim.run(args.warmup)
+        sim.sync()
+        ms = sim.run_timed(args.steps)
+        mlups = args.nx * args.ny * args.steps / (ms * 1e-3) / 1e6
+        print(f"V={V} tpb={tpb} streaming={st}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
+              f"{mlups*72/1e3:,.0f} GB/s  {mlups*72/1e3/peak*100:.1f}% of measured HBM copy", flush=True)
+    print(sim.info())
+    sim.close()
+
+
+if __name__ == "__main__":
+    main()
