@@ -1,0 +1,408 @@
+#!/usr/bin/env python3
+"""bench.py — MLUPS of the D2Q9-BGK time step on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (N GPUs, weak scaling): BASELINE.json configs[4], the synthetic 16384-wide channel of
+SURVEY.md §8(d): every rank holds a 16384 x 16384 row slab of a 16384 x (16384*N) grid (channel
+walls on the global first/last row, 64x64 solid blocks every 1024 cells), one process per GPU, halo
+rows exchanged inside the step kernel through CUDA-IPC peer memory.  A "step" is one LBM time step of
+the whole grid.  `value` = cells * K / device time (CUDA events on the launching stream, max over
+ranks) with the lattice resident in HBM; `e2e` = the reference's own timed region
+(d2q9-bgk.c:196-263: upload + K steps + sync + download) through the C-ABI with pinned HOST buffers.
+
+--impl reference times the reference's algorithm on the box's host cores: the OpenMP fp32 CPU
+restatement in oracle/ (the reference's OpenCL host cannot be built in this image), each step one
+time step of a bounded 16384-wide sample of the same deck.
+
+Prints exactly ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+NX = 16384
+ROWS_PER_GPU = 16384
+BYTES_PER_UPDATE = 72  # 9 fp32 reads + 9 fp32 writes per cell update
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch(kernel_name: str, cells: int):
+    """DRAM bytes per launch of the step kernel from the committed ncu --set full capture
+    (profiles/step_kernel_traffic.json, written by tools/ncu_summary.py); None if not captured for
+    this kernel/grid."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as fp:
+            rec = json.load(fp)
+        if rec.get("cells_per_launch") == cells and rec.get("kernel") == kernel_name:
+            return float(rec["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reason_bits = [], 0
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # CUDA_VISIBLE_DEVICES may renumber; NVML index follows the physical order
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis:
+                ids = [v for v in vis.split(",") if v != ""]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            self.err = str(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                try:
+                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        reasons = [n for n, b in {**self.BAD, **self.NOTE}.items() if self.reason_bits & b]
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def channel_free_cells(lbm, nx, ny):
+    return lbm.decks.synthetic_channel_free_cells(nx, ny)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle = the checker / CPU baseline; never on the product path)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_sample_deck(lbm, ny):
+    p, cells, obstacles = lbm.decks.synthetic_channel(NX, ny)
+    return p, cells, obstacles
+
+
+def time_oracle(lbm, ny, steps, warmup, variant="fastest"):
+    """Times `steps` oracle time steps (accelerate + timestep, OpenMP over rows) on a NX x ny sample.
+    Returns (seconds per step list, threads)."""
+    import ctypes as C
+    import oracle_lib
+    lib = oracle_lib.load(variant)
+    p, cells, obstacles = cpu_sample_deck(lbm, ny)
+    op = oracle_lib.to_oracle_params(p)
+    a = np.ascontiguousarray(cells)
+    b = np.empty_like(a)
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    ip = obstacles.ctypes.data_as(C.POINTER(C.c_int))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        lib.oracle_f32_accelerate(C.byref(op), fp(a), ip)
+        lib.oracle_f32_timestep(C.byref(op), fp(a), fp(b), ip, 0)
+        dt = time.perf_counter() - t0
+        a, b = b, a
+        if i >= warmup:
+            times.append(dt)
+    return times, int(lib.oracle_num_threads())
+
+
+def cpu_baseline(lbm, budget_s=15.0):
+    """The oracle port on this box's host cores, bounded to ~budget_s of CPU work."""
+    ny = 1024
+    t1, threads = time_oracle(lbm, ny, 1, 1)
+    steps = int(max(3, min(100, budget_s / max(t1[0], 1e-3))))
+    times, threads = time_oracle(lbm, ny, steps, 0)
+    mlups = NX * ny * len(times) / sum(times) / 1e6
+    return {"value": round(mlups, 1), "unit": "MLUPS", "cores": threads, "kind": "port",
+            "sample": f"{len(times)} time steps of a {NX}x{ny} slab of the same synthetic channel "
+                      f"(oracle/lbm_oracle.c fp32, gcc -O3 -fopenmp -mavx2 if available, "
+                      f"OMP threads = {threads})"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's algorithm on host cores (oracle port; see module docstring)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import opencl_lattice_boltzmann_b200 as lbm
+    import oracle_lib
+    oracle_lib.build_oracle()
+    # size the per-step sample so that warmup+steps finish in about two minutes
+    t_probe, threads = time_oracle(lbm, 256, 1, 1)
+    rate = NX * 256 / t_probe[0]  # cells per second
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    ny = int(max(64, min(ROWS_PER_GPU, (rate * budget / NX) // 64 * 64)))
+    times, threads = time_oracle(lbm, ny, args.steps, args.warmup)
+    total = sum(times)
+    mlups = NX * ny * len(times) / total / 1e6
+    sample = (f"each step = one time step (accelerate + fused propagate/rebound/collision/av_vels) of a "
+              f"{NX}x{ny} slab of the synthetic channel on {threads} OpenMP threads")
+    line = {
+        "impl": "reference", "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * total / len(times), 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"synthetic {NX}x{ROWS_PER_GPU} channel per GPU (BASELINE configs[4]); "
+                               f"CPU arm steps a bounded {NX}x{ny} sample of it",
+                   "nx": NX, "ny_sample": ny},
+        "cpu_baseline": {"value": round(mlups, 1), "unit": "MLUPS", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(mlups, 1), "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import opencl_lattice_boltzmann_b200 as lbm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} processes (one per GPU)")
+        raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nx, rows = NX, args.rows_per_gpu
+    ny_global = rows * world
+    y0 = rank * rows
+
+    # ---- the deck: this rank's slab of the global synthetic channel, in pinned host memory ----
+    t0 = time.time()
+    free_cells = channel_free_cells(lbm, nx, ny_global)
+    p = lbm.decks.Params(nx=nx, ny=ny_global, maxIters=args.steps, reynolds_dim=10,
+                         density=float(np.float32(0.1)), accel=float(np.float32(0.005)),
+                         omega=float(np.float32(1.85)))
+    p.free_cells_inv = float(np.float32(1.0) / np.float32(free_cells))
+    cells_h = torch.empty((9, rows, nx), dtype=torch.float32, pin_memory=True)
+    obst_h = torch.empty((rows, nx), dtype=torch.int32, pin_memory=True)
+    init = lbm.decks.initial_cells(lbm.decks.Params(nx=1, ny=1, maxIters=0, reynolds_dim=10, density=p.density,
+                                                    accel=p.accel, omega=p.omega))
+    for k in range(9):
+        cells_h[k].fill_(float(init[k, 0, 0]))
+    obst_h.copy_(torch.from_numpy(lbm.decks.synthetic_channel_rows(nx, ny_global, y0, rows)))
+    out_h = torch.empty((9, rows, nx), dtype=torch.float32, pin_memory=True)
+    log(f"[rank {rank}] deck {nx}x{rows} of {nx}x{ny_global} built in {time.time() - t0:.1f}s")
+
+    # ---- context, ring ----
+    sim = lbm.cabi.Simulation(p, slab=(local_rank, rank, world, y0, rows))
+    if world > 1:
+        blobs = [None] * world
+        dist.all_gather_object(blobs, sim.export_blob())
+        sim.connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+
+    def upload():
+        sim.upload(cells_h, obst_h)
+        if world > 1:
+            sim.halo_push()
+            barrier()
+
+    # ---- value: lattice resident in HBM ----
+    upload()
+    barrier()
+    if args.warmup > 0:
+        sim.run(args.warmup)
+        sim.sync()
+    info0 = sim.info()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms = sim.run_timed(args.steps)
+    barrier()
+    clocks = sampler.stop()
+    info1 = sim.info()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    cells_total = nx * ny_global
+    mlups = cells_total * args.steps / (ms * 1e-3) / 1e6
+    launches = int(info1["kernel_launches"] - info0["kernel_launches"])
+
+    # per-rank av_vels -> deterministic cross-GPU combine (rank order, error-free sums)
+    nav = args.warmup + args.steps
+    hi, lo = sim.download_av_sums(nav)
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (hi, lo))
+        hi_all = np.stack([x[0] for x in parts])
+        lo_all = np.stack([x[1] for x in parts])
+    else:
+        hi_all, lo_all = hi[None], lo[None]
+    av = lbm.cabi.combine_av_sums(hi_all, lo_all, p.free_cells_inv)
+    if not np.all(np.isfinite(av)) or not np.all(av[1:] > 0):
+        raise SystemExit(f"av_vels look wrong: {av[:5]}")
+
+    # ---- e2e: the reference's timed region through the C-ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    sim.upload(cells_h, obst_h)
+    if world > 1:
+        sim.halo_push()
+        barrier()
+    sim.run(args.steps)
+    sim.sync()
+    sim.download_cells(out_h)
+    hi2, lo2 = sim.download_av_sums(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_mlups = cells_total * args.steps / e2e_s / 1e6
+    h2d = (cells_h.numel() * 4 + obst_h.numel() * 4) * world
+    d2h = (out_h.numel() * 4 + 2 * 8 * args.steps) * world
+    checksum = float(out_h[:, ::257, ::263].double().sum())
+    if not np.isfinite(checksum):
+        raise SystemExit("final state is not finite")
+
+    sim.close()
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        per_gpu_cells = nx * rows
+        achieved = BYTES_PER_UPDATE * per_gpu_cells / (ms / args.steps * 1e-3) / 1e9  # GB/s per GPU
+        kname = info1["kernel_name"]
+        line = {
+            "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"synthetic {nx}x{rows} channel per GPU (BASELINE.json configs[4]): "
+                            f"global {nx}x{ny_global}, walls + 64x64 blocks every 1024 cells",
+                "nx": nx, "ny_global": ny_global, "rows_per_gpu": rows,
+                "decomposition": f"{world} row slab(s), one process per GPU, in-kernel halo stores over CUDA-IPC peer memory",
+                "kernel": kname,
+                "l2": f"no flush needed: the two lattices are {2 * 36 * per_gpu_cells / 2**30:.1f} GiB per GPU, "
+                      f"far larger than the 126 MB L2",
+                "e2e_region": f"upload + {args.steps} steps + sync + download (d2q9-bgk.c:196-263), pinned host buffers",
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4),
+                "traffic": ncu_traffic_per_launch(kname, per_gpu_cells),
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * per_gpu_cells,
+                "launch_ms": round(ms / args.steps, 5),
+                "note": "per GPU; launch duration = CUDA-event time of the K step launches / K "
+                        "(includes 1 accelerate pre-pass and the av_vels finalize launches)",
+            },
+            "e2e": {"value": round(e2e_mlups, 1), "unit": "MLUPS", "h2d_bytes_per_step": h2d // args.steps,
+                    "d2h_bytes_per_step": d2h // args.steps, "seconds": round(e2e_s, 4)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "av_vels_last": float(av[-1]),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(lbm)
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU,
+                    help="rows of the 16384-wide channel per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

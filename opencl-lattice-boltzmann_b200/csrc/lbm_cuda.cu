@@ -73,7 +73,11 @@ struct Slab {
   float* arena = nullptr;
   ArenaLayout layout{};
   uint32_t* mask = nullptr;
-  float* partials = nullptr;
+  double2* partials = nullptr;   // chunk_steps x blocks_per_step block partials
+  double2* scratch = nullptr;    // chunk_steps x splits range sums of av_finalize_kernel
+  unsigned int* tickets = nullptr;
+  long long blocks = 0;          // step-kernel blocks = partials per step
+  int splits = 1;
   double* av_hi = nullptr;
   double* av_lo = nullptr;
   long long av_capacity = 0;
@@ -158,12 +162,17 @@ void resolve_options(lbm_ctx* ctx) {
   if (tpb != 128 && tpb != 256 && tpb != 512) tpb = 256;
   ctx->tpb = tpb;
   ctx->segs = (nx + 32 * V - 1) / (32 * V);
-  const double lattice_bytes = 2.0 * 9.0 * 4.0 * (double)ctx->pitch * (double)(ctx->rows + 2);
-  ctx->streaming = ctx->opt_streaming >= 0 ? (ctx->opt_streaming != 0) : (lattice_bytes > 96.0 * 1024 * 1024);
+  // cache-hint mode of the lattice accesses (lbm_kernels.cuh); plain ld.global.nc / st.global measured best
+  ctx->streaming = (ctx->opt_streaming >= 0 && ctx->opt_streaming <= 4) ? ctx->opt_streaming : 0;
   long long per_step = 0;
-  for (auto& s : ctx->slabs) per_step = std::max(per_step, (long long)s.rows * ctx->segs);
+  const int wpb = tpb / 32;
+  for (auto& s : ctx->slabs) {
+    s.blocks = ((long long)s.rows * ctx->segs + wpb - 1) / wpb;
+    s.splits = (int)std::max(1LL, std::min(64LL, s.blocks / 2048));
+    per_step = std::max(per_step, s.blocks);
+  }
   ctx->per_step = per_step;
-  long long chunk = ctx->opt_chunk > 0 ? ctx->opt_chunk : (64LL << 20) / (4 * std::max(1LL, per_step));
+  long long chunk = ctx->opt_chunk > 0 ? ctx->opt_chunk : (64LL << 20) / (16 * std::max(1LL, per_step));
   ctx->chunk_steps = (int)std::max(1LL, std::min(chunk, 4096LL));
 }
 
@@ -213,7 +222,10 @@ int ensure_partials(lbm_ctx* ctx) {
   for (auto& s : ctx->slabs) {
     if (s.partials) continue;
     if (set_device(s)) return 1;
-    CK(cudaMalloc(&s.partials, sizeof(float) * (size_t)ctx->chunk_steps * (size_t)s.rows * (size_t)ctx->segs));
+    CK(cudaMalloc(&s.partials, sizeof(double2) * (size_t)ctx->chunk_steps * (size_t)s.blocks));
+    CK(cudaMalloc(&s.scratch, sizeof(double2) * (size_t)ctx->chunk_steps * (size_t)s.splits));
+    CK(cudaMalloc(&s.tickets, sizeof(unsigned int) * (size_t)ctx->chunk_steps));
+    CK(cudaMemsetAsync(s.tickets, 0, sizeof(unsigned int) * (size_t)ctx->chunk_steps, s.stream));
   }
   return 0;
 }
@@ -296,28 +308,32 @@ int create_common(lbm_ctx** out, const lbm_params* p, int nslabs, const int* dev
   return 0;
 }
 
-template <int V, bool STREAM, int TPB>
-void launch_step_t(const lbm::StepArgs& a, long long warps, cudaStream_t st) {
-  const long long blocks = (warps + TPB / 32 - 1) / (TPB / 32);
-  lbm::step_kernel<V, STREAM, TPB><<<(unsigned)blocks, TPB, 0, st>>>(a);
+template <int V, int HINT, int TPB>
+void launch_step_t(const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  lbm::step_kernel<V, HINT, TPB><<<(unsigned)blocks, TPB, 0, st>>>(a);
 }
 
-template <int V, bool STREAM>
-void launch_step_v(int tpb, const lbm::StepArgs& a, long long warps, cudaStream_t st) {
-  if (tpb == 128) launch_step_t<V, STREAM, 128>(a, warps, st);
-  else if (tpb == 512) launch_step_t<V, STREAM, 512>(a, warps, st);
-  else launch_step_t<V, STREAM, 256>(a, warps, st);
+template <int V, int HINT>
+void launch_step_v(int tpb, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  if (tpb == 128) launch_step_t<V, HINT, 128>(a, blocks, st);
+  else if (tpb == 512) launch_step_t<V, HINT, 512>(a, blocks, st);
+  else launch_step_t<V, HINT, 256>(a, blocks, st);
 }
 
-void launch_step(int V, int streaming, int tpb, const lbm::StepArgs& a, long long warps, cudaStream_t st) {
-  if (streaming) {
-    if (V == 4) launch_step_v<4, true>(tpb, a, warps, st);
-    else if (V == 2) launch_step_v<2, true>(tpb, a, warps, st);
-    else launch_step_v<1, true>(tpb, a, warps, st);
-  } else {
-    if (V == 4) launch_step_v<4, false>(tpb, a, warps, st);
-    else if (V == 2) launch_step_v<2, false>(tpb, a, warps, st);
-    else launch_step_v<1, false>(tpb, a, warps, st);
+template <int HINT>
+void launch_step_h(int V, int tpb, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  if (V == 4) launch_step_v<4, HINT>(tpb, a, blocks, st);
+  else if (V == 2) launch_step_v<2, HINT>(tpb, a, blocks, st);
+  else launch_step_v<1, HINT>(tpb, a, blocks, st);
+}
+
+void launch_step(int V, int hint, int tpb, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  switch (hint) {
+    case 1: launch_step_h<1>(V, tpb, a, blocks, st); break;
+    case 2: launch_step_h<2>(V, tpb, a, blocks, st); break;
+    case 3: launch_step_h<3>(V, tpb, a, blocks, st); break;
+    case 4: launch_step_h<4>(V, tpb, a, blocks, st); break;
+    default: launch_step_h<0>(V, tpb, a, blocks, st); break;
   }
 }
 
@@ -398,7 +414,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
       a.up_plane_stride = s.up.layout.plane_stride;
       a.down_ghost = nb_ghost_above(s.down, ctx->cur ^ 1);
       a.down_plane_stride = s.down.layout.plane_stride;
-      a.partials = s.partials + (long long)in_chunk * s.rows * ctx->segs;
+      a.partials = s.partials + (long long)in_chunk * s.blocks;
       if (ctx->ring) {
         unsigned long long* f = s.flags();
         a.flag_from_up = f + 0;
@@ -410,7 +426,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         a.edge_target = s.step_launches * (unsigned long long)ctx->segs;
       }
       a.epoch = ctx->epoch;
-      launch_step(ctx->V, ctx->streaming, ctx->tpb, a, (long long)s.rows * ctx->segs, s.stream);
+      launch_step(ctx->V, ctx->streaming, ctx->tpb, a, s.blocks, s.stream);
       ctx->launches++;
     }
     ctx->cur ^= 1;
@@ -418,8 +434,8 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
     if (in_chunk == ctx->chunk_steps || last) {
       for (auto& s : ctx->slabs) {
         if (set_device(s)) return 1;
-        lbm::av_finalize_kernel<<<in_chunk, 256, 0, s.stream>>>(s.partials, (long long)s.rows * ctx->segs, s.av_hi,
-                                                                  s.av_lo, chunk_first);
+        lbm::av_finalize_kernel<<<dim3(s.splits, in_chunk), 256, 0, s.stream>>>(s.partials, s.blocks, s.scratch, s.tickets,
+                                                                                 s.av_hi, s.av_lo, chunk_first);
         ctx->launches++;
       }
       chunk_first += in_chunk;
@@ -596,7 +612,7 @@ void lbm_destroy(lbm_ctx* ctx) {
     if (s.down.ipc && s.down.arena) cudaIpcCloseMemHandle(s.down.arena);
     if (s.arena) cudaFree(s.arena);
     if (s.mask) cudaFree(s.mask);
-    if (s.partials) cudaFree(s.partials);
+    if (s.partials) { cudaFree(s.partials); cudaFree(s.scratch); cudaFree(s.tickets); }
     if (s.av_hi) cudaFree(s.av_hi);
     if (s.av_lo) cudaFree(s.av_lo);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
@@ -618,6 +634,8 @@ int lbm_upload(lbm_ctx* ctx, const float* cells_soa, const int* obstacles) {
     if (s.partials) {  // geometry options may have changed
       if (set_device(s)) return 1;
       CK(cudaFree(s.partials));
+      CK(cudaFree(s.scratch));
+      CK(cudaFree(s.tickets));
       s.partials = nullptr;
     }
   const int nx = ctx->p.nx;
@@ -758,16 +776,15 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "chunk_steps")) ctx->opt_chunk = (int)value;
   else return fail("unknown option '%s'", key);
   if (sync_all(ctx)) return 1;
-  const int old_chunk = ctx->chunk_steps;
-  const long long old_per_step = ctx->per_step;
   resolve_options(ctx);
-  if (ctx->chunk_steps != old_chunk || ctx->per_step != old_per_step)
-    for (auto& s : ctx->slabs)
-      if (s.partials) {
-        if (set_device(s)) return 1;
-        CK(cudaFree(s.partials));
-        s.partials = nullptr;
-      }
+  for (auto& s : ctx->slabs)  // partial geometry may have changed
+    if (s.partials) {
+      if (set_device(s)) return 1;
+      CK(cudaFree(s.partials));
+      CK(cudaFree(s.scratch));
+      CK(cudaFree(s.tickets));
+      s.partials = nullptr;
+    }
   return 0;
 }
 
@@ -788,7 +805,7 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
   info->steps_done = ctx->steps_done;
   info->kernel_launches = ctx->launches;
   info->partials_per_step = ctx->per_step;
-  snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,stream=%d,tpb=%d>", ctx->V,
+  snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d>", ctx->V,
            ctx->streaming, ctx->tpb);
   return 0;
 }

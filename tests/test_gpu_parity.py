@@ -35,7 +35,7 @@ def test_lattice_bit_exact_vs_oracle(lbm, oracle, nx, ny):
 
 @pytest.mark.parametrize("V", [1, 2, 4])
 @pytest.mark.parametrize("tpb", [128, 256, 512])
-@pytest.mark.parametrize("streaming", [0, 1])
+@pytest.mark.parametrize("streaming", [0, 1, 2, 3, 4])
 def test_kernel_variants_bit_exact(lbm, oracle, V, tpb, streaming):
     p, cells, obstacles = random_case(384, 24, seed=7, walls=False)  # open edges: y wrap carries fluid
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 5)

@@ -1,0 +1,67 @@
+"""Summarise an ncu report into profiles/: the raw-page CSV of the step kernel (selected metrics)
+and profiles/step_kernel_traffic.json (DRAM bytes per launch, read by bench.py's roofline.traffic).
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep r01 [cells_per_launch]
+"""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEEP = [
+    "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__bytes.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "l1tex__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__maximum_warps_per_active_cycle_pct", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "launch__waves_per_multiprocessor", "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.sum",
+    "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio",
+    "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio",
+]
+
+
+def main():
+    rep, tag = sys.argv[1], sys.argv[2]
+    cells = int(sys.argv[3]) if len(sys.argv) > 3 else 16384 * 16384
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = [hdr.index(k) for k in KEEP if k in hdr]
+    out = os.path.join(ROOT, "profiles", f"{tag}_step_kernel_ncu_full.csv")
+    with open(out, "w", newline="") as fp:
+        w = csv.writer(fp)
+        w.writerow(["metric", "unit"] + [f"launch{i}" for i in range(len(data))])
+        for i in idx:
+            w.writerow([hdr[i], units[i]] + [r[i] for r in data])
+    print("wrote", out)
+
+    def col(name):
+        i = hdr.index(name)
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+        return [float(r[i]) * scale for r in data]
+
+    rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+    per_launch = sum(a + b for a, b in zip(rd, wr)) / len(rd)
+    kname = data[0][hdr.index("Kernel Name")]
+    # "void step_kernel<4, 1, 256>(StepArgs)" -> bench.py's info name
+    import re
+    m = re.search(r"step_kernel<(\d+), (\d+), (\d+)>", kname)
+    name = f"step_kernel<V={m.group(1)},hint={m.group(2)},tpb={m.group(3)}>" if m else kname
+    rec = {"kernel": name, "ncu_kernel_name": kname, "cells_per_launch": cells,
+           "dram_bytes_read_per_launch": sum(rd) / len(rd), "dram_bytes_write_per_launch": sum(wr) / len(wr),
+           "dram_bytes_per_launch": per_launch, "algorithmic_bytes_per_launch": 72 * cells,
+           "traffic_over_algorithmic": per_launch / (72 * cells), "launches_captured": len(rd),
+           "source": f"ncu --set full --clock-control none, {os.path.basename(rep)} ({tag})"}
+    with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json"), "w") as fp:
+        json.dump(rec, fp, indent=1)
+    print(json.dumps(rec, indent=1))
+
+
+if __name__ == "__main__":
+    main()

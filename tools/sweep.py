@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--ny", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--variants", default="4:256:1,4:128:1,4:512:1,2:256:1,2:128:1,1:256:1,4:256:0")
+    ap.add_argument("--variants", default="4:256:0,4:256:1,4:256:2,4:256:3,4:256:4,4:128:0,4:512:0,4:128:2,2:256:0,1:256:0")
     args = ap.parse_args()
     peak = 6546.2
     try:
@@ -41,7 +41,7 @@ def main():
         sim.sync()
         ms = sim.run_timed(args.steps)
         mlups = args.nx * args.ny * args.steps / (ms * 1e-3) / 1e6
-        print(f"V={V} tpb={tpb} streaming={st}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
+        print(f"V={V} tpb={tpb} hint={st}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
               f"{mlups*72/1e3:,.0f} GB/s  {mlups*72/1e3/peak*100:.1f}% of measured HBM copy", flush=True)
     print(sim.info())
     sim.close()
