@@ -145,6 +145,7 @@ def time_oracle(lbm, ny, steps, warmup, variant="fastest"):
     import ctypes as C
     import oracle_lib
     lib = oracle_lib.load(variant)
+    lib.oracle_set_num_threads(oracle_lib.host_threads())  # all host cores, whatever OMP_NUM_THREADS says
     p, cells, obstacles = cpu_sample_deck(lbm, ny)
     op = oracle_lib.to_oracle_params(p)
     a = np.ascontiguousarray(cells)

@@ -8,6 +8,7 @@ directory, whose name has a hyphen).
 """
 from . import decks  # noqa: F401
 from . import cabi  # noqa: F401
+from . import ring  # noqa: F401
 from .build import build_all  # noqa: F401
 
-__all__ = ["decks", "cabi", "build_all"]
+__all__ = ["decks", "cabi", "ring", "build_all"]

@@ -122,7 +122,8 @@ def final_state_fields(params: Params, cells: np.ndarray, obstacles: np.ndarray)
     with np.errstate(divide="ignore", invalid="ignore"):
         u_x = (cells[1] + cells[5] + cells[8] - cells[3] - cells[6] - cells[7]) / local_density
         u_y = (cells[2] + cells[5] + cells[6] - cells[4] - cells[7] - cells[8]) / local_density
-    u = np.sqrt(u_x.astype(np.float64) ** 2 + u_y.astype(np.float64) ** 2).astype(np.float32)
+    with np.errstate(invalid="ignore"):  # fp32 sum of squares, double sqrt, as d2q9-bgk.c:828
+        u = np.sqrt(((u_x * u_x) + (u_y * u_y)).astype(np.float64)).astype(np.float32)
     pressure = local_density * c_sq
     u_x = np.where(blocked, np.float32(0), u_x)
     u_y = np.where(blocked, np.float32(0), u_y)

@@ -34,6 +34,15 @@ int oracle_num_threads(void)
 #endif
 }
 
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------ */
 /* fp32: kernels.cl                                                          */
 /* ------------------------------------------------------------------------ */

@@ -99,6 +99,7 @@ void oracle_f64_pressure(const oracle_params64 *p, const double *cells, const in
                          double *pressure);
 
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

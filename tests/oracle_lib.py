@@ -28,6 +28,14 @@ def build_oracle() -> None:
                    stdout=subprocess.DEVNULL)
 
 
+def host_threads() -> int:
+    """Cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arms undo that)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def _cpu_has_avx2() -> bool:
     try:
         with open("/proc/cpuinfo") as fp:
@@ -78,6 +86,8 @@ def load(variant: str = "base"):
     lib.oracle_f64_pressure.restype = None
     lib.oracle_num_threads.argtypes = []
     lib.oracle_num_threads.restype = C.c_int
+    lib.oracle_set_num_threads.argtypes = [C.c_int]
+    lib.oracle_set_num_threads.restype = None
     _lib_cache[variant] = lib
     return lib
 
