@@ -76,6 +76,10 @@ struct Slab {
   double2* partials = nullptr;   // chunk_steps x blocks_per_step block partials
   double2* scratch = nullptr;    // chunk_steps x splits range sums of av_finalize_kernel
   unsigned int* tickets = nullptr;
+  unsigned long long* barrier = nullptr;   // grid-barrier ticket of the persistent kernel
+  unsigned long long barrier_base = 0;
+  long long pblocks = 0;                   // grid of the persistent kernel
+  long long partial_capacity = 0;          // double2 entries in `partials`
   long long blocks = 0;          // step-kernel blocks = partials per step
   int splits = 1;
   double* av_hi = nullptr;
@@ -121,7 +125,7 @@ struct lbm_ctx {
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0;
   // resolved
-  int V = 1, tpb = 256, streaming = 0, chunk_steps = 1, segs = 1;
+  int V = 1, tpb = 256, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
   long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
   float w1 = 0.f, w2 = 0.f;
 };
@@ -154,12 +158,23 @@ int validate(const lbm_params* p) {
 
 void resolve_options(lbm_ctx* ctx) {
   const int nx = ctx->p.nx;
+  // L2-resident single-slab lattices run many steps per (cooperative) launch
+  const double lattice_bytes = 2.0 * 9.0 * 4.0 * (double)ctx->pitch * (double)(ctx->rows + 2);
+  const bool can_persist = ctx->slabs.size() == 1 && ctx->nranks == 1;
+  ctx->persistent = can_persist && (ctx->opt_persistent >= 0 ? ctx->opt_persistent != 0
+                                                              : lattice_bytes <= 96.0 * 1024 * 1024);
   int V = ctx->opt_v;
-  if (V != 1 && V != 2 && V != 4) V = 4;
+  if (V != 1 && V != 2 && V != 4) {
+    V = 4;
+    // latency-bound small grids: fewer cells per thread until ~1024 warps are in flight
+    // (measured on the check decks: 128x128 -> 1, 256x256 -> 2, 1024x1024 -> 4)
+    if (ctx->persistent)
+      while (V > 1 && (long long)nx * ctx->rows / (32 * V) < 1024) V >>= 1;
+  }
   while (V > 1 && nx % V != 0) V >>= 1;
   ctx->V = V;
   int tpb = ctx->opt_tpb;
-  if (tpb != 128 && tpb != 256 && tpb != 512) tpb = 256;
+  if (tpb != 128 && tpb != 256 && tpb != 512) tpb = ctx->persistent ? 128 : 256;
   ctx->tpb = tpb;
   ctx->segs = (nx + 32 * V - 1) / (32 * V);
   // cache-hint mode of the lattice accesses (lbm_kernels.cuh); plain ld.global.nc / st.global measured best
@@ -222,10 +237,16 @@ int ensure_partials(lbm_ctx* ctx) {
   for (auto& s : ctx->slabs) {
     if (s.partials) continue;
     if (set_device(s)) return 1;
-    CK(cudaMalloc(&s.partials, sizeof(double2) * (size_t)ctx->chunk_steps * (size_t)s.blocks));
+    s.partial_capacity = (long long)ctx->chunk_steps * s.blocks;
+    CK(cudaMalloc(&s.partials, sizeof(double2) * (size_t)s.partial_capacity));
     CK(cudaMalloc(&s.scratch, sizeof(double2) * (size_t)ctx->chunk_steps * (size_t)s.splits));
     CK(cudaMalloc(&s.tickets, sizeof(unsigned int) * (size_t)ctx->chunk_steps));
     CK(cudaMemsetAsync(s.tickets, 0, sizeof(unsigned int) * (size_t)ctx->chunk_steps, s.stream));
+    if (!s.barrier) {
+      CK(cudaMalloc(&s.barrier, sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(s.barrier, 0, sizeof(unsigned long long), s.stream));
+      s.barrier_base = 0;
+    }
   }
   return 0;
 }
@@ -337,6 +358,53 @@ void launch_step(int V, int hint, int tpb, const lbm::StepArgs& a, long long blo
   }
 }
 
+
+template <int V, int TPB>
+int persistent_grid_t(int device, long long blocks_needed, long long* grid) {
+  int per_sm = 0, sms = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::persistent_kernel<V, TPB>, TPB, 0));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  *grid = std::max(1LL, std::min(blocks_needed, (long long)per_sm * sms));
+  return 0;
+}
+
+template <int V, int TPB>
+int launch_persistent_t(const lbm::PersistArgs& pa, long long grid, cudaStream_t st) {
+  void* args[] = {const_cast<lbm::PersistArgs*>(&pa)};
+  CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lbm::persistent_kernel<V, TPB>), dim3((unsigned)grid),
+                                 dim3(TPB), args, 0, st));
+  return 0;
+}
+
+#define LBM_DISPATCH_V_TPB(V_, TPB_, CALL)                                  \
+  do {                                                                      \
+    if ((V_) == 4) {                                                        \
+      if ((TPB_) == 128) return CALL(4, 128);                               \
+      if ((TPB_) == 512) return CALL(4, 512);                               \
+      return CALL(4, 256);                                                  \
+    } else if ((V_) == 2) {                                                 \
+      if ((TPB_) == 128) return CALL(2, 128);                               \
+      if ((TPB_) == 512) return CALL(2, 512);                               \
+      return CALL(2, 256);                                                  \
+    } else {                                                                \
+      if ((TPB_) == 128) return CALL(1, 128);                               \
+      if ((TPB_) == 512) return CALL(1, 512);                               \
+      return CALL(1, 256);                                                  \
+    }                                                                       \
+  } while (0)
+
+int persistent_grid(int V, int tpb, int device, long long blocks_needed, long long* grid) {
+#define CALL_(v, t) persistent_grid_t<v, t>(device, blocks_needed, grid)
+  LBM_DISPATCH_V_TPB(V, tpb, CALL_);
+#undef CALL_
+}
+
+int launch_persistent(int V, int tpb, const lbm::PersistArgs& pa, long long grid, cudaStream_t st) {
+#define CALL_(v, t) launch_persistent_t<v, t>(pa, grid, st)
+  LBM_DISPATCH_V_TPB(V, tpb, CALL_);
+#undef CALL_
+}
+
 // local row of global row ny-2 in this slab, or -1
 int accel_row_of(const lbm_ctx* ctx, const Slab& s) {
   const int g = ctx->p.ny - 2;
@@ -389,9 +457,59 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
     }
   }
 
+  if (ctx->persistent) {
+    // one cooperative launch per chunk of steps; grid barrier between steps (lbm_kernels.cuh)
+    Slab& s = ctx->slabs[0];
+    if (set_device(s)) return 1;
+    const int wpb = ctx->tpb / 32;
+    if (persistent_grid(ctx->V, ctx->tpb, s.device, ((long long)s.rows * ctx->segs + wpb - 1) / wpb, &s.pblocks))
+      return 1;
+    const long long max_steps = std::max(1LL, std::min<long long>(ctx->chunk_steps, s.partial_capacity / s.pblocks));
+    auto fill = [&](lbm::StepArgs& a, int src_buf) {
+      a.src = s.row0(src_buf);
+      a.dst = s.row0(src_buf ^ 1);
+      a.plane_stride = s.layout.plane_stride;
+      a.pitch = ctx->pitch;
+      a.nx = ctx->p.nx;
+      a.rows = s.rows;
+      a.segs = ctx->segs;
+      a.mask = s.mask;
+      a.mask_pitch = ctx->mask_pitch;
+      a.omega = ctx->p.omega;
+      a.w1 = ctx->w1;
+      a.w2 = ctx->w2;
+      a.accel_row = -1;
+      a.up_ghost = nb_ghost_below(s.up, src_buf ^ 1);
+      a.up_plane_stride = s.up.layout.plane_stride;
+      a.down_ghost = nb_ghost_above(s.down, src_buf ^ 1);
+      a.down_plane_stride = s.down.layout.plane_stride;
+    };
+    long long first = ctx->steps_since_upload;
+    for (int done = 0; done < nsteps;) {
+      const int n = (int)std::min<long long>(max_steps, nsteps - done);
+      lbm::PersistArgs pa{};
+      fill(pa.even, ctx->cur);
+      fill(pa.odd, ctx->cur ^ 1);
+      pa.nsteps = n;
+      pa.accel_row = accel_row_of(ctx, s);
+      pa.skip_last_accel = (done + n == nsteps) ? 1 : 0;
+      pa.barrier = s.barrier;
+      pa.barrier_base = s.barrier_base;
+      pa.partials = s.partials;
+      if (launch_persistent(ctx->V, ctx->tpb, pa, s.pblocks, s.stream)) return 1;
+      s.barrier_base += (unsigned long long)n * (unsigned long long)s.pblocks;
+      lbm::av_finalize_kernel<<<dim3(1, n), 256, 0, s.stream>>>(s.partials, s.pblocks, s.scratch, s.tickets, s.av_hi,
+                                                                 s.av_lo, first);
+      ctx->launches += 2;
+      ctx->cur ^= (n & 1);
+      first += n;
+      done += n;
+    }
+  }
+
   int in_chunk = 0;
   long long chunk_first = ctx->steps_since_upload;
-  for (int t = 0; t < nsteps; t++) {
+  for (int t = 0; !ctx->persistent && t < nsteps; t++) {
     ctx->epoch++;
     const bool last = (t == nsteps - 1);
     for (auto& s : ctx->slabs) {
@@ -613,6 +731,7 @@ void lbm_destroy(lbm_ctx* ctx) {
     if (s.arena) cudaFree(s.arena);
     if (s.mask) cudaFree(s.mask);
     if (s.partials) { cudaFree(s.partials); cudaFree(s.scratch); cudaFree(s.tickets); }
+    if (s.barrier) cudaFree(s.barrier);
     if (s.av_hi) cudaFree(s.av_hi);
     if (s.av_lo) cudaFree(s.av_lo);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
@@ -801,12 +920,15 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
   info->cells_per_thread = ctx->V;
   info->threads_per_block = ctx->tpb;
   info->streaming = ctx->streaming;
-  info->steps_per_launch = 1;
+  info->steps_per_launch = ctx->persistent ? ctx->chunk_steps : 1;
   info->steps_done = ctx->steps_done;
   info->kernel_launches = ctx->launches;
   info->partials_per_step = ctx->per_step;
-  snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d>", ctx->V,
-           ctx->streaming, ctx->tpb);
+  if (ctx->persistent)
+    snprintf(info->kernel_name, sizeof info->kernel_name, "persistent_kernel<V=%d,tpb=%d>", ctx->V, ctx->tpb);
+  else
+    snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d>", ctx->V,
+             ctx->streaming, ctx->tpb);
   return 0;
 }
 

@@ -567,3 +567,29 @@ void oracle_f64_pressure(const oracle_params64 *p, const double *cells, const in
     }
   }
 }
+
+/* d2q9-bgk.c:789-831 in double, for regenerating the final_state goldens the
+ * reference repository stripped (.MISSING_LARGE_BLOBS). */
+void oracle_f64_final_state(const oracle_params64 *p, const double *cells, const int *obstacles,
+                            double *u_x_out, double *u_y_out, double *u_out, double *pressure_out)
+{
+  const double c_sq = 1.0 / 3.0;
+  const size_t plane = (size_t)p->nx * p->ny;
+  for (size_t c = 0; c < plane; c++) {
+    if (obstacles[c]) {
+      u_x_out[c] = u_y_out[c] = u_out[c] = 0.0;
+      pressure_out[c] = p->density * c_sq;
+      continue;
+    }
+    double d = 0.0;
+    for (int kk = 0; kk < NSPEEDS; kk++) d += cells[kk * plane + c];
+    const double u_x = (cells[1 * plane + c] + cells[5 * plane + c] + cells[8 * plane + c]
+                        - (cells[3 * plane + c] + cells[6 * plane + c] + cells[7 * plane + c])) / d;
+    const double u_y = (cells[2 * plane + c] + cells[5 * plane + c] + cells[6 * plane + c]
+                        - (cells[4 * plane + c] + cells[7 * plane + c] + cells[8 * plane + c])) / d;
+    u_x_out[c] = u_x;
+    u_y_out[c] = u_y;
+    u_out[c] = sqrt((u_x * u_x) + (u_y * u_y));
+    pressure_out[c] = d * c_sq;
+  }
+}

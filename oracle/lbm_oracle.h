@@ -98,6 +98,9 @@ double oracle_f64_av_velocity(const oracle_params64 *p, const double *cells, con
 void oracle_f64_pressure(const oracle_params64 *p, const double *cells, const int *obstacles,
                          double *pressure);
 
+void oracle_f64_final_state(const oracle_params64 *p, const double *cells, const int *obstacles,
+                            double *u_x, double *u_y, double *u, double *pressure);
+
 int oracle_num_threads(void);
 void oracle_set_num_threads(int n);
 

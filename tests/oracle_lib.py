@@ -84,6 +84,8 @@ def load(variant: str = "base"):
     lib.oracle_f64_av_velocity.restype = C.c_double
     lib.oracle_f64_pressure.argtypes = [P64, dp, ip, dp]
     lib.oracle_f64_pressure.restype = None
+    lib.oracle_f64_final_state.argtypes = [P64, dp, ip, dp, dp, dp, dp]
+    lib.oracle_f64_final_state.restype = None
     lib.oracle_num_threads.argtypes = []
     lib.oracle_num_threads.restype = C.c_int
     lib.oracle_set_num_threads.argtypes = [C.c_int]
@@ -135,6 +137,18 @@ def run_f64(params, cells, obstacles, nsteps):
     pressure = np.empty((params.ny, params.nx), dtype=np.float64)
     lib.oracle_f64_pressure(C.byref(op), _dp(cells), _ip(obstacles), _dp(pressure))
     return cells, av[:nsteps], pressure
+
+
+def final_state_f64(params, cells, obstacles):
+    """(u_x, u_y, u, pressure) of an fp64 state, d2q9-bgk.c:789-831 in double."""
+    lib = load("base")
+    op = OracleParams64(params.density, params.accel, params.omega, params.nx, params.ny,
+                        params.maxIters, params.reynolds_dim)
+    cells = np.ascontiguousarray(cells, dtype=np.float64)
+    obstacles = np.ascontiguousarray(obstacles, dtype=np.int32)
+    outs = [np.empty((params.ny, params.nx), dtype=np.float64) for _ in range(4)]
+    lib.oracle_f64_final_state(C.byref(op), _dp(cells), _ip(obstacles), *[_dp(o) for o in outs])
+    return outs
 
 
 def final_state_f32(params, cells, obstacles):

@@ -40,8 +40,37 @@ def test_kernel_variants_bit_exact(lbm, oracle, V, tpb, streaming):
     p, cells, obstacles = random_case(384, 24, seed=7, walls=False)  # open edges: y wrap carries fluid
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 5)
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 5,
-                                      options={"cells_per_thread": V, "threads_per_block": tpb, "streaming": streaming})
+                                      options={"cells_per_thread": V, "threads_per_block": tpb, "streaming": streaming,
+                                               "persistent": 0})
     assert info["cells_per_thread"] == V and info["threads_per_block"] == tpb and info["streaming"] == streaming
+    assert info["kernel_name"].startswith("step_kernel")
+    assert np.array_equal(bits(got_cells), bits(ref_cells))
+    np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("V", [1, 2, 4])
+@pytest.mark.parametrize("tpb", [128, 256, 512])
+def test_persistent_kernel_bit_exact(lbm, oracle, V, tpb):
+    """The multi-step cooperative kernel (grid barrier between steps) against the oracle and against
+    the one-launch-per-step kernel; 37 steps with chunk_steps=8 also crosses launch boundaries."""
+    p, cells, obstacles = random_case(384, 24, seed=7, walls=False)
+    ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 37)
+    opts = {"cells_per_thread": V, "threads_per_block": tpb, "persistent": 1, "chunk_steps": 8}
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 37, options=opts)
+    assert info["kernel_name"].startswith("persistent_kernel")
+    assert np.array_equal(bits(got_cells), bits(ref_cells))
+    np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
+    # same segment size (cells_per_thread) => bitwise the same averages as one launch per step
+    one_cells, one_av, _ = run_gpu(lbm, p, cells, obstacles, 37, options={"persistent": 0, "cells_per_thread": V})
+    assert np.array_equal(bits(got_cells), bits(one_cells)) and np.array_equal(bits(got_av), bits(one_av))
+
+
+def test_persistent_grid_larger_than_device(lbm, oracle):
+    """More warp segments than co-resident warps: blocks loop over several segments per step."""
+    p, cells, obstacles = random_case(2048, 1024, seed=21)
+    ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 4)
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 4, options={"persistent": 1, "cells_per_thread": 1})
+    assert info["kernel_name"].startswith("persistent_kernel")
     assert np.array_equal(bits(got_cells), bits(ref_cells))
     np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
 
@@ -66,8 +95,8 @@ def test_row_slabs_on_one_gpu_equal_single(lbm, nslabs):
     """The multi-slab path (ghost rows, edge stores into the neighbour, epoch flags) on ONE device:
     lattice and av_vels bitwise equal to the single-slab run."""
     p, cells, obstacles = random_case(256, 41, seed=11, walls=False)
-    a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 9)
-    b_cells, b_av, info = run_gpu(lbm, p, cells, obstacles, 9, devices=[0] * nslabs)
+    a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 9, options={"cells_per_thread": 4})
+    b_cells, b_av, info = run_gpu(lbm, p, cells, obstacles, 9, devices=[0] * nslabs, options={"cells_per_thread": 4})
     assert info["nslabs"] == nslabs
     assert np.array_equal(bits(a_cells), bits(b_cells))
     assert np.array_equal(bits(a_av), bits(b_av))
