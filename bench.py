@@ -243,6 +243,10 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
 
     nx, rows = NX, args.rows_per_gpu
+    if args.scaling == "strong":       # total work fixed: the 16384-row grid split into N slabs
+        rows = args.rows_per_gpu // world
+        if rows * world != args.rows_per_gpu:
+            raise SystemExit(f"--scaling strong needs {args.rows_per_gpu} rows divisible by {world} GPUs")
     ny_global = rows * world
     y0 = rank * rows
 
@@ -347,7 +351,7 @@ def run_b200_arm(args):
         line = {
             "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {
                 "workload": f"synthetic {nx}x{rows} channel per GPU (BASELINE.json configs[4]): "
@@ -396,6 +400,9 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU,
                     help="rows of the 16384-wide channel per GPU (default: the BASELINE config)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak (default, the driver's contract): rows-per-gpu rows on every GPU; "
+                         "strong: rows-per-gpu rows in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.steps < 1:

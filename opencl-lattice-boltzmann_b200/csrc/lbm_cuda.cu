@@ -200,10 +200,13 @@ int alloc_slab(lbm_ctx* ctx, Slab& s) {
   s.layout.buf_floats = 9 * s.layout.plane_stride;
   s.layout.flags_offset = 2 * s.layout.buf_floats * (long long)sizeof(float);
   const size_t arena_bytes = (size_t)s.layout.flags_offset + 256;
+  // stream-ordered clears: a plain cudaMemset runs on the legacy stream, which the slab's
+  // non-blocking stream does not wait for, and could still be clearing when lbm_upload copies
   CK(cudaMalloc(&s.arena, arena_bytes));
-  CK(cudaMemset(s.arena, 0, arena_bytes));
+  CK(cudaMemsetAsync(s.arena, 0, arena_bytes, s.stream));
   CK(cudaMalloc(&s.mask, sizeof(uint32_t) * (size_t)ctx->mask_pitch * s.rows));
-  CK(cudaMemset(s.mask, 0, sizeof(uint32_t) * (size_t)ctx->mask_pitch * s.rows));
+  CK(cudaMemsetAsync(s.mask, 0, sizeof(uint32_t) * (size_t)ctx->mask_pitch * s.rows, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   CK(cudaEventCreate(&s.ev_start));
   CK(cudaEventCreate(&s.ev_stop));
   return 0;
@@ -364,7 +367,11 @@ int persistent_grid_t(int device, long long blocks_needed, long long* grid) {
   int per_sm = 0, sms = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::persistent_kernel<V, TPB>, TPB, 0));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  *grid = std::max(1LL, std::min(blocks_needed, (long long)per_sm * sms));
+  // Balanced static schedule: every block loops over the same number k of block-sized groups of
+  // warp segments (a grid of all co-resident blocks would leave most of them idle in the last pass).
+  const long long resident = std::max(1LL, (long long)per_sm * sms);
+  const long long k = (blocks_needed + resident - 1) / resident;
+  *grid = std::max(1LL, (blocks_needed + k - 1) / k);
   return 0;
 }
 

@@ -34,7 +34,7 @@ def main():
 
     p, cells, obstacles = helpers.random_case(args.nx, args.ny, seed=4242, walls=False)
     y0, rows = lbm.cabi.partition_rows(args.ny, world, rank)
-    sim = lbm.cabi.Simulation(p, slab=(local, rank, world, y0, rows))
+    sim = lbm.cabi.Simulation(p, slab=(local, rank, world, y0, rows), options={"cells_per_thread": 4})
     blobs = [None] * world
     dist.all_gather_object(blobs, sim.export_blob())
     sim.connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
@@ -62,8 +62,9 @@ def main():
         ref_cells, ref_av = oracle_lib.run_f32(p, cells, obstacles, args.steps)
         same = np.array_equal(helpers.bits(full), helpers.bits(ref_cells))
         av_ok = np.allclose(av, ref_av, rtol=2e-6, atol=0)
-        # single-slab run on this GPU: av_vels must be bitwise identical to the ring's
-        with lbm.cabi.Simulation(p, devices=[local]) as one:
+        # single-slab run on this GPU (same cells per thread = same segment sums): av_vels must be
+        # bitwise identical to the ring's
+        with lbm.cabi.Simulation(p, devices=[local], options={"cells_per_thread": 4}) as one:
             one.upload(cells, obstacles)
             one.run(args.steps)
             one.sync()

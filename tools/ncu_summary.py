@@ -26,7 +26,48 @@ KEEP = [
 ]
 
 
+def deck_summary(rep, tag, nx, ny, steps):
+    """L2-resident deck captures: writes profiles/<tag>_ncu.csv with the L2 / DRAM figures per step."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    r = data[0]
+
+    def val(name):
+        i = hdr.index(name)
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9,
+                 "s": 1.0, "sector": 1.0, "%": 1.0, "inst": 1.0, "register/thread": 1.0}.get(units[i], 1.0)
+        return float(r[i]) * scale
+
+    dur = val("gpu__time_duration.sum")
+    l2_bytes = 32.0 * (val("lts__t_sectors_srcunit_tex_op_read.sum") + val("lts__t_sectors_srcunit_tex_op_write.sum"))
+    dram = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+    cells = nx * ny
+    rec = {
+        "kernel": r[hdr.index("Kernel Name")], "grid": r[hdr.index("Grid Size")], "block": r[hdr.index("Block Size")],
+        "deck": f"{nx}x{ny}", "steps_in_launch": steps, "duration_us": dur * 1e6, "us_per_step": dur * 1e6 / steps,
+        "mlups": cells * steps / dur / 1e6,
+        "algorithmic_gbs": 72.0 * cells * steps / dur / 1e9,
+        "l2_bytes_from_sm": l2_bytes, "l2_gbs": l2_bytes / dur / 1e9,
+        "l2_bytes_over_algorithmic": l2_bytes / (72.0 * cells * steps),
+        "l2_hit_rate_pct": val("lts__t_sector_hit_rate.pct"),
+        "lts_throughput_pct_of_peak": val("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+        "dram_bytes": dram, "dram_gbs": dram / dur / 1e9,
+        "dram_read_bytes": val("dram__bytes_read.sum"), "dram_write_bytes": val("dram__bytes_write.sum"),
+        "registers_per_thread": val("launch__registers_per_thread"),
+        "warps_active_pct": val("sm__warps_active.avg.pct_of_peak_sustained_active"),
+        "sm_throughput_pct": val("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+        "source": f"ncu --set full --clock-control none, {os.path.basename(rep)}",
+    }
+    out = os.path.join(ROOT, "profiles", f"{tag}_ncu.json")
+    with open(out, "w") as fp:
+        json.dump(rec, fp, indent=1)
+    print(json.dumps(rec, indent=1))
+
+
 def main():
+    if sys.argv[1] == "--deck":
+        return deck_summary(sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]))
     rep, tag = sys.argv[1], sys.argv[2]
     cells = int(sys.argv[3]) if len(sys.argv) > 3 else 16384 * 16384
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
