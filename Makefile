@@ -14,7 +14,7 @@ LIB  = $(PKG)/liblbm_b200.so
 HOSTCC   ?= /usr/bin/gcc
 NVCC     ?= nvcc
 PYTHON   ?= python
-CFLAGS    = -std=c99 -Wall -O3 -D_DEFAULT_SOURCE
+CFLAGS    = -std=c99 -Wall -O3 -fopenmp -D_DEFAULT_SOURCE
 NVCCFLAGS = -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wall
 LIBS      = -lm
 

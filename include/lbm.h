@@ -114,6 +114,12 @@ int lbm_halo_push(lbm_ctx *ctx);
  * the CURRENT buffer (the reference reads ocl.cells whatever the parity). */
 int lbm_download_cells(lbm_ctx *ctx, float *cells_soa);
 
+/* Output stage: the four per-cell fields write_values() prints
+ * (d2q9-bgk.c:789-831: u_x, u_y, |u|, pressure; obstacle cells 0,0,0,density/3), computed on
+ * the device from the current state with the host code's exact fp32 arithmetic and copied to
+ * rows*nx host floats each.  Any pointer may be NULL to skip that field. */
+int lbm_download_final_state(lbm_ctx *ctx, float *u_x, float *u_y, float *u, float *pressure);
+
 /* Replaces clEnqueueReadBuffer(ocl.avgs) (d2q9-bgk.c:257-260): the first n
  * per-step averages since the last lbm_upload.  Single-process contexts only
  * (all slabs local); multi-process callers use lbm_download_av_sums. */
@@ -152,6 +158,9 @@ int lbm_run_timed(lbm_ctx *ctx, int nsteps, float *ms);
  * "chunk_steps".  Unknown key -> non-zero. */
 int lbm_set_option(lbm_ctx *ctx, const char *key, long value);
 int lbm_get_info(lbm_ctx *ctx, lbm_info *info);
+/* Debug canary: number of non-zero floats in the pad columns [nx, pitch) of every row of both
+ * lattice buffers (cleared at creation, never written by a correct kernel). */
+int lbm_debug_pad_nonzero(lbm_ctx *ctx, long long *count);
 int lbm_device_count(void);
 int lbm_abi_version(void);
 

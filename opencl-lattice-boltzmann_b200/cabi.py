@@ -19,8 +19,8 @@ LIB_PATH = os.path.join(PKG_DIR, "liblbm_b200.so")
 EXPORTS = [
     "lbm_create", "lbm_create_on", "lbm_create_slab", "lbm_partition_rows", "lbm_export_size", "lbm_export",
     "lbm_connect", "lbm_destroy", "lbm_upload", "lbm_halo_push", "lbm_download_cells", "lbm_download_av_vels",
-    "lbm_download_av_sums", "lbm_combine_av_sums", "lbm_host_alloc", "lbm_host_free", "lbm_run", "lbm_sync",
-    "lbm_run_timed", "lbm_set_option", "lbm_get_info", "lbm_device_count", "lbm_abi_version", "lbm_last_error",
+    "lbm_download_av_sums", "lbm_download_final_state", "lbm_combine_av_sums", "lbm_host_alloc", "lbm_host_free", "lbm_run", "lbm_sync",
+    "lbm_run_timed", "lbm_set_option", "lbm_get_info", "lbm_debug_pad_nonzero", "lbm_device_count", "lbm_abi_version", "lbm_last_error",
 ]
 
 
@@ -73,6 +73,7 @@ def load_library(path: str | None = None):
     lib.lbm_download_cells.argtypes = [vp, vp]
     lib.lbm_download_av_vels.argtypes = [vp, fp, C.c_int]
     lib.lbm_download_av_sums.argtypes = [vp, dp, dp, C.c_int]
+    lib.lbm_download_final_state.argtypes = [vp, vp, vp, vp, vp]
     lib.lbm_combine_av_sums.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_float, fp]
     lib.lbm_combine_av_sums.restype = None
     lib.lbm_host_alloc.argtypes = [C.c_size_t]
@@ -84,6 +85,7 @@ def load_library(path: str | None = None):
     lib.lbm_run_timed.argtypes = [vp, C.c_int, fp]
     lib.lbm_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     lib.lbm_get_info.argtypes = [vp, C.POINTER(LbmInfo)]
+    lib.lbm_debug_pad_nonzero.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.lbm_device_count.argtypes = []
     lib.lbm_abi_version.argtypes = []
     lib.lbm_last_error.argtypes = []
@@ -160,6 +162,11 @@ class Simulation:
         d["kernel_name"] = info.kernel_name.decode()
         return d
 
+    def pad_nonzero(self) -> int:
+        n = C.c_longlong(0)
+        self._ck(self.lib.lbm_debug_pad_nonzero(self._ctx, C.byref(n)))
+        return int(n.value)
+
     # -- ring plumbing ---------------------------------------------------------
     def export_blob(self) -> bytes:
         buf = C.create_string_buffer(self.lib.lbm_export_size())
@@ -220,6 +227,12 @@ class Simulation:
         dp = C.POINTER(C.c_double)
         self._ck(self.lib.lbm_download_av_sums(self._ctx, hi.ctypes.data_as(dp), lo.ctypes.data_as(dp), n))
         return hi[:n], lo[:n]
+
+    def download_final_state(self):
+        """(u_x, u_y, u, pressure), each [rows, nx] float32, computed on the device (d2q9-bgk.c:789-831)."""
+        outs = [np.empty((self.rows, self.params.nx), dtype=np.float32) for _ in range(4)]
+        self._ck(self.lib.lbm_download_final_state(self._ctx, *[self._ptr(o) for o in outs]))
+        return outs
 
     def close(self):
         if self._ctx:

@@ -823,6 +823,38 @@ int lbm_download_cells(lbm_ctx* ctx, float* cells_soa) {
   return sync_all(ctx);
 }
 
+int lbm_download_final_state(lbm_ctx* ctx, float* u_x, float* u_y, float* u, float* pressure) {
+  if (!ctx) return fail("ctx is NULL");
+  if (!ctx->uploaded) return fail("lbm_download_final_state before lbm_upload");
+  float* host[4] = {u_x, u_y, u, pressure};
+  const int nx = ctx->p.nx;
+  for (auto& s : ctx->slabs) {
+    if (set_device(s)) return 1;
+    // bounded staging: at most ~64 Mi cells per field at a time
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(s.rows, (64LL << 20) / std::max(1, nx)));
+    float* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int f = 0; f < 4; f++)
+      if (host[f]) CK(cudaMalloc(&dev[f], sizeof(float) * (size_t)chunk * nx));
+    for (int r0 = 0; r0 < s.rows; r0 += chunk) {
+      const int nr = std::min(chunk, s.rows - r0);
+      dim3 grid((nx + 255) / 256, nr);
+      lbm::final_state_kernel<<<grid, 256, 0, s.stream>>>(s.row0(ctx->cur), s.layout.plane_stride, ctx->pitch, nx, r0,
+                                                          s.mask, ctx->mask_pitch, ctx->p.density, dev[0], dev[1], dev[2],
+                                                          dev[3]);
+      ctx->launches++;
+      const size_t off = ((size_t)(s.y0 - ctx->y0) + r0) * nx;
+      for (int f = 0; f < 4; f++)
+        if (host[f])
+          CK(cudaMemcpyAsync(host[f] + off, dev[f], sizeof(float) * (size_t)nr * nx, cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+    }
+    for (int f = 0; f < 4; f++)
+      if (dev[f]) CK(cudaFree(dev[f]));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int lbm_download_av_sums(lbm_ctx* ctx, double* hi, double* lo, int n) {
   if (!ctx || !hi || !lo) return fail("lbm_download_av_sums: NULL argument");
   if (n < 0 || n > ctx->steps_since_upload) return fail("asked for %d averages, %lld steps run", n, ctx->steps_since_upload);
@@ -911,6 +943,27 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
       CK(cudaFree(s.tickets));
       s.partials = nullptr;
     }
+  return 0;
+}
+
+int lbm_debug_pad_nonzero(lbm_ctx* ctx, long long* count) {
+  // Out-of-bounds canary (compute-sanitizer is not available on the GPU pool): the arena is
+  // cleared at creation and no kernel may ever write the pad columns [nx, pitch) of any row
+  // (ghost rows included) of either buffer; counts the floats there that are no longer 0.
+  if (!ctx || !count) return fail("lbm_debug_pad_nonzero: NULL argument");
+  *count = 0;
+  const int pad = ctx->pitch - ctx->p.nx;
+  if (pad == 0) return 0;
+  if (sync_all(ctx)) return 1;
+  for (auto& s : ctx->slabs) {
+    if (set_device(s)) return 1;
+    const size_t nrows = (size_t)2 * 9 * (s.rows + 2);
+    std::vector<float> host(nrows * pad);
+    CK(cudaMemcpy2D(host.data(), sizeof(float) * pad, s.arena + ctx->p.nx, sizeof(float) * ctx->pitch,
+                    sizeof(float) * pad, nrows, cudaMemcpyDeviceToHost));
+    for (float v : host)
+      if (v != 0.0f) (*count)++;
+  }
   return 0;
 }
 

@@ -16,7 +16,8 @@
  * The timed region is the reference's: upload + loop + sync + download (:196-263).
  * Environment: LBM_NGPUS=N splits the rows into N slabs on devices 0..N-1
  * (LBM_DEVICES=a,b,.. picks ordinals; the reference had OCL_DEVICE, :920-929);
- * LBM_QUIET=1 suppresses the extra throughput lines after the reference's five.
+ * LBM_QUIET=1 suppresses the extra throughput lines after the reference's five;
+ * LBM_FINAL_STATE=text|binary|none picks the final_state.dat form (text = the reference's).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -89,7 +90,19 @@ int main(int argc, char *argv[])
            info.kernel_launches);
   }
 
-  write_values(&params, cells, obstacles, av_vels);
+  /* write_values(), d2q9-bgk.c:276.  The per-cell fields come from the device output stage
+   * (bit-identical to the host maths); LBM_HOST_FIELDS=1 computes them on the host instead. */
+  if (getenv("LBM_HOST_FIELDS")) {
+    write_values(&params, cells, obstacles, av_vels);
+  } else {
+    const size_t ncells = (size_t)params.nx * (size_t)params.ny;
+    float *fields = (float *)malloc(sizeof(float) * 4 * ncells);
+    if (fields == NULL) die("cannot allocate memory for the output fields", __LINE__, __FILE__);
+    check(lbm_download_final_state(ctx, fields, fields + ncells, fields + 2 * ncells, fields + 3 * ncells),
+          "reading final state fields", __LINE__);
+    write_fields(&params, fields, fields + ncells, fields + 2 * ncells, fields + 3 * ncells, obstacles, av_vels);
+    free(fields);
+  }
   lbm_destroy(ctx);
   free_deck(cells, obstacles, av_vels);
   return EXIT_SUCCESS;

@@ -156,36 +156,92 @@ float calc_reynolds(const lbm_params *params, const float *cells, const int *obs
   return av_velocity(params, cells, obstacles) * params->reynolds_dim / viscosity;
 }
 
-int write_values(const lbm_params *params, const float *cells, const int *obstacles, const float *av_vels)
+/* One text row of final_state.dat into buf; returns the bytes written.  Line format of
+ * d2q9-bgk.c:835: x y u_x u_y |u| pressure obstacle. */
+static size_t format_row(char *buf, int ii, int nx, const float *u_x, const float *u_y, const float *u,
+                         const float *pressure, const int *obstacles)
 {
-  const float c_sq = 1.0f / 3.0f;
-  const size_t ncells = (size_t)params->nx * (size_t)params->ny;
-  FILE *fp = fopen(FINALSTATEFILE, "w");
-  if (fp == NULL) die("could not open file output file", __LINE__, __FILE__);
-  static char iobuf[1 << 20];
-  setvbuf(fp, iobuf, _IOFBF, sizeof iobuf);
+  size_t n = 0;
+  for (int jj = 0; jj < nx; jj++)
+    n += (size_t)sprintf(buf + n, "%d %d %.12E %.12E %.12E %.12E %d\n", jj, ii, u_x[jj], u_y[jj], u[jj],
+                         pressure[jj], obstacles[jj]);
+  return n;
+}
 
-  for (int ii = 0; ii < params->ny; ii++) {
-    for (int jj = 0; jj < params->nx; jj++) {
-      const size_t c = (size_t)ii * params->nx + jj;
-      float u_x = 0.0f, u_y = 0.0f, u = 0.0f, pressure;
-      if (obstacles[c]) {
-        pressure = params->density * c_sq; /* d2q9-bgk.c:794-798 */
-      } else {
-        float local_density;
-        cell_moments(cells, ncells, c, &local_density, &u_x, &u_y);
-        u = sqrt((u_x * u_x) + (u_y * u_y));
-        pressure = local_density * c_sq;   /* d2q9-bgk.c:829-831 */
+#define ROW_BYTES_PER_CELL 128 /* > 2*11 + 4*20 + 7 */
+
+int write_fields(const lbm_params *params, const float *u_x, const float *u_y, const float *u,
+                 const float *pressure, const int *obstacles, const float *av_vels)
+{
+  const int nx = params->nx, ny = params->ny;
+  const char *mode = getenv("LBM_FINAL_STATE");
+  if (mode == NULL) mode = "text";
+
+  if (strcmp(mode, "none") != 0) {
+    FILE *fp = fopen(FINALSTATEFILE, "w");
+    if (fp == NULL) die("could not open file output file", __LINE__, __FILE__);
+    if (strcmp(mode, "binary") == 0) {
+      /* for grids whose text file would be tens of GB: header "LBMFS1 nx ny\n" then u_x, u_y, |u|,
+       * pressure (fp32) and the obstacle map (int32), each ny*nx, row-major */
+      const size_t ncells = (size_t)nx * (size_t)ny;
+      fprintf(fp, "LBMFS1 %d %d\n", nx, ny);
+      fwrite(u_x, sizeof(float), ncells, fp);
+      fwrite(u_y, sizeof(float), ncells, fp);
+      fwrite(u, sizeof(float), ncells, fp);
+      fwrite(pressure, sizeof(float), ncells, fp);
+      fwrite(obstacles, sizeof(int), ncells, fp);
+    } else {
+      /* rows are formatted in parallel (exact printf semantics), written in order */
+      int block = (int)((64u << 20) / ((size_t)nx * ROW_BYTES_PER_CELL));
+      if (block < 1) block = 1;
+      if (block > ny) block = ny;
+      char *buf = (char *)malloc((size_t)block * nx * ROW_BYTES_PER_CELL);
+      size_t *len = (size_t *)malloc(sizeof(size_t) * (size_t)block);
+      if (buf == NULL || len == NULL) die("cannot allocate memory for the output buffer", __LINE__, __FILE__);
+      for (int i0 = 0; i0 < ny; i0 += block) {
+        const int nb = (ny - i0 < block) ? ny - i0 : block;
+#pragma omp parallel for schedule(static)
+        for (int b = 0; b < nb; b++) {
+          const size_t off = (size_t)(i0 + b) * nx;
+          len[b] = format_row(buf + (size_t)b * nx * ROW_BYTES_PER_CELL, i0 + b, nx, u_x + off, u_y + off, u + off,
+                              pressure + off, obstacles + off);
+        }
+        for (int b = 0; b < nb; b++) fwrite(buf + (size_t)b * nx * ROW_BYTES_PER_CELL, 1, len[b], fp);
       }
-      /* x y u_x u_y |u| pressure obstacle, d2q9-bgk.c:835 */
-      fprintf(fp, "%d %d %.12E %.12E %.12E %.12E %d\n", jj, ii, u_x, u_y, u, pressure, obstacles[c]);
+      free(buf);
+      free(len);
     }
+    fclose(fp);
   }
-  fclose(fp);
 
-  fp = fopen(AVVELSFILE, "w");
+  FILE *fp = fopen(AVVELSFILE, "w");
   if (fp == NULL) die("could not open file output file", __LINE__, __FILE__);
   for (int ii = 0; ii < params->maxIters; ii++) fprintf(fp, "%d:\t%.12E\n", ii, av_vels[ii]); /* :850 */
   fclose(fp);
   return EXIT_SUCCESS;
+}
+
+int write_values(const lbm_params *params, const float *cells, const int *obstacles, const float *av_vels)
+{
+  /* d2q9-bgk.c:772-856 with the fields computed on the host, as the reference does */
+  const float c_sq = 1.0f / 3.0f;
+  const size_t ncells = (size_t)params->nx * (size_t)params->ny;
+  float *f = (float *)malloc(sizeof(float) * 4 * ncells);
+  if (f == NULL) die("cannot allocate memory for the output fields", __LINE__, __FILE__);
+  float *u_x = f, *u_y = f + ncells, *u = f + 2 * ncells, *pressure = f + 3 * ncells;
+#pragma omp parallel for schedule(static)
+  for (size_t c = 0; c < ncells; c++) {
+    u_x[c] = u_y[c] = u[c] = 0.0f;
+    if (obstacles[c]) {
+      pressure[c] = params->density * c_sq; /* d2q9-bgk.c:794-798 */
+    } else {
+      float local_density;
+      cell_moments(cells, ncells, c, &local_density, &u_x[c], &u_y[c]);
+      u[c] = sqrt((u_x[c] * u_x[c]) + (u_y[c] * u_y[c]));
+      pressure[c] = local_density * c_sq;   /* d2q9-bgk.c:829-831 */
+    }
+  }
+  const int rc = write_fields(params, u_x, u_y, u, pressure, obstacles, av_vels);
+  free(f);
+  return rc;
 }

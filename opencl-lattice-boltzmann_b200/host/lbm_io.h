@@ -30,7 +30,13 @@ void free_deck(float *cells, int *obstacles, float *av_vels);
 float av_velocity(const lbm_params *params, const float *cells, const int *obstacles);
 float calc_reynolds(const lbm_params *params, const float *cells, const int *obstacles);
 
-/* write_values() (d2q9-bgk.c:772-856): final_state.dat and av_vels.dat in the CWD */
+/* write_values() (d2q9-bgk.c:772-856): final_state.dat and av_vels.dat in the CWD, fields computed
+ * on the host from the cells as the reference does */
 int write_values(const lbm_params *params, const float *cells, const int *obstacles, const float *av_vels);
+
+/* Same files from fields already computed (lbm_download_final_state).  Rows are formatted in
+ * parallel.  LBM_FINAL_STATE=text (default) | binary | none selects the final_state.dat form. */
+int write_fields(const lbm_params *params, const float *u_x, const float *u_y, const float *u,
+                 const float *pressure, const int *obstacles, const float *av_vels);
 
 #endif

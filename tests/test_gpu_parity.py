@@ -154,6 +154,36 @@ def test_full_row_length_slab_vs_oracle(lbm, oracle):
     np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
 
 
+@pytest.mark.parametrize("nx,ny,opts", [(100, 37, {}), (34, 9, {}), (33, 5, {}), (100, 37, {"persistent": 0}),
+                                        (130, 40, {"persistent": 0, "cells_per_thread": 2}), (1, 4, {})])
+def test_pad_columns_never_written(lbm, nx, ny, opts):
+    """Out-of-bounds canary (no compute-sanitizer on the pool): pad columns [nx, pitch) stay zero, also
+    for the multi-slab ring whose edge rows are stored into neighbours' ghost rows."""
+    p, cells, obstacles = random_case(nx, ny, seed=17)
+    for kw in ({}, {"devices": [0, 0, 0]} if ny >= 3 else {}):
+        with lbm.cabi.Simulation(p, options=opts, **kw) as sim:
+            sim.upload(cells, obstacles)
+            sim.run(9)
+            sim.sync()
+            assert sim.info()["pitch"] > nx
+            assert sim.pad_nonzero() == 0
+
+
+@pytest.mark.parametrize("nx,ny,kw", [(128, 128, {}), (100, 37, {}), (256, 41, {"devices": [0, 0, 0]})])
+def test_final_state_fields_on_device(lbm, oracle, nx, ny, kw):
+    """Output stage on the GPU == the host maths of write_values (d2q9-bgk.c:789-831), bit for bit."""
+    p, cells, obstacles = random_case(nx, ny, seed=31)
+    with lbm.cabi.Simulation(p, **kw) as sim:
+        sim.upload(cells, obstacles)
+        sim.run(6)
+        sim.sync()
+        got_cells = sim.download_cells()
+        fields = sim.download_final_state()
+    ref = oracle.final_state_f32(p, got_cells, obstacles)
+    for name, g, r in zip(("u_x", "u_y", "u", "pressure"), fields, ref):
+        assert np.array_equal(bits(g), bits(r)), name
+
+
 def test_errors_are_loud(lbm):
     p, cells, obstacles = random_case(64, 8)
     with lbm.cabi.Simulation(p) as sim:
