@@ -76,9 +76,10 @@ struct Slab {
   double2* partials = nullptr;   // chunk_steps x blocks_per_step block partials
   double2* scratch = nullptr;    // chunk_steps x splits range sums of av_finalize_kernel
   unsigned int* tickets = nullptr;
-  unsigned long long* barrier = nullptr;   // grid-barrier ticket of the persistent kernel
-  unsigned long long barrier_base = 0;
+  unsigned int* progress = nullptr;        // per-block step counters of the persistent kernel
+  long long progress_capacity = 0;
   long long pblocks = 0;                   // grid of the persistent kernel
+  int rows_per_block = 1;
   long long partial_capacity = 0;          // double2 entries in `partials`
   long long blocks = 0;          // step-kernel blocks = partials per step
   int splits = 1;
@@ -123,7 +124,7 @@ struct lbm_ctx {
   long long steps_since_upload = 0;
   long long launches = 0;
   // options
-  int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0;
+  int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0;
   // resolved
   int V = 1, tpb = 256, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
   long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
@@ -240,16 +241,13 @@ int ensure_partials(lbm_ctx* ctx) {
   for (auto& s : ctx->slabs) {
     if (s.partials) continue;
     if (set_device(s)) return 1;
-    s.partial_capacity = (long long)ctx->chunk_steps * s.blocks;
+    // the persistent kernel has at most one block per row, the step kernel s.blocks blocks
+    s.partial_capacity = (long long)ctx->chunk_steps * std::max<long long>(s.blocks, ctx->persistent ? s.rows : 0);
     CK(cudaMalloc(&s.partials, sizeof(double2) * (size_t)s.partial_capacity));
     CK(cudaMalloc(&s.scratch, sizeof(double2) * (size_t)ctx->chunk_steps * (size_t)s.splits));
     CK(cudaMalloc(&s.tickets, sizeof(unsigned int) * (size_t)ctx->chunk_steps));
     CK(cudaMemsetAsync(s.tickets, 0, sizeof(unsigned int) * (size_t)ctx->chunk_steps, s.stream));
-    if (!s.barrier) {
-      CK(cudaMalloc(&s.barrier, sizeof(unsigned long long)));
-      CK(cudaMemsetAsync(s.barrier, 0, sizeof(unsigned long long), s.stream));
-      s.barrier_base = 0;
-    }
+
   }
   return 0;
 }
@@ -363,15 +361,15 @@ void launch_step(int V, int hint, int tpb, const lbm::StepArgs& a, long long blo
 
 
 template <int V, int TPB>
-int persistent_grid_t(int device, long long blocks_needed, long long* grid) {
+int persistent_grid_t(int device, int rows, long long* grid, int* rows_per_block) {
+  // block b owns rows [b*rpb, (b+1)*rpb): as many blocks as can be co-resident (cooperative launch)
   int per_sm = 0, sms = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::persistent_kernel<V, TPB>, TPB, 0));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  // Balanced static schedule: every block loops over the same number k of block-sized groups of
-  // warp segments (a grid of all co-resident blocks would leave most of them idle in the last pass).
   const long long resident = std::max(1LL, (long long)per_sm * sms);
-  const long long k = (blocks_needed + resident - 1) / resident;
-  *grid = std::max(1LL, (blocks_needed + k - 1) / k);
+  const int rpb = (int)std::max(1LL, (rows + resident - 1) / resident);
+  *rows_per_block = rpb;
+  *grid = (rows + rpb - 1) / rpb;
   return 0;
 }
 
@@ -400,8 +398,8 @@ int launch_persistent_t(const lbm::PersistArgs& pa, long long grid, cudaStream_t
     }                                                                       \
   } while (0)
 
-int persistent_grid(int V, int tpb, int device, long long blocks_needed, long long* grid) {
-#define CALL_(v, t) persistent_grid_t<v, t>(device, blocks_needed, grid)
+int persistent_grid(int V, int tpb, int device, int rows, long long* grid, int* rows_per_block) {
+#define CALL_(v, t) persistent_grid_t<v, t>(device, rows, grid, rows_per_block)
   LBM_DISPATCH_V_TPB(V, tpb, CALL_);
 #undef CALL_
 }
@@ -468,9 +466,13 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
     // one cooperative launch per chunk of steps; grid barrier between steps (lbm_kernels.cuh)
     Slab& s = ctx->slabs[0];
     if (set_device(s)) return 1;
-    const int wpb = ctx->tpb / 32;
-    if (persistent_grid(ctx->V, ctx->tpb, s.device, ((long long)s.rows * ctx->segs + wpb - 1) / wpb, &s.pblocks))
-      return 1;
+    if (persistent_grid(ctx->V, ctx->tpb, s.device, s.rows, &s.pblocks, &s.rows_per_block)) return 1;
+    if (s.progress_capacity < s.pblocks) {
+      if (s.progress) CK(cudaFree(s.progress));
+      CK(cudaMalloc(&s.progress, sizeof(unsigned int) * 32 * (size_t)s.pblocks));
+      s.progress_capacity = s.pblocks;
+    }
+    if (s.partial_capacity < s.pblocks) return fail("internal: partial buffer smaller than the persistent grid");
     const long long max_steps = std::max(1LL, std::min<long long>(ctx->chunk_steps, s.partial_capacity / s.pblocks));
     auto fill = [&](lbm::StepArgs& a, int src_buf) {
       a.src = s.row0(src_buf);
@@ -500,14 +502,15 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
       pa.nsteps = n;
       pa.accel_row = accel_row_of(ctx, s);
       pa.skip_last_accel = (done + n == nsteps) ? 1 : 0;
-      pa.barrier = s.barrier;
-      pa.barrier_base = s.barrier_base;
+      pa.rows_per_block = s.rows_per_block;
+      pa.progress = s.progress;
       pa.partials = s.partials;
+      pa.global_barrier = ctx->opt_sync;
+      CK(cudaMemsetAsync(s.progress, 0, sizeof(unsigned int) * 32 * (size_t)s.pblocks, s.stream));
       if (launch_persistent(ctx->V, ctx->tpb, pa, s.pblocks, s.stream)) return 1;
-      s.barrier_base += (unsigned long long)n * (unsigned long long)s.pblocks;
       lbm::av_finalize_kernel<<<dim3(1, n), 256, 0, s.stream>>>(s.partials, s.pblocks, s.scratch, s.tickets, s.av_hi,
                                                                  s.av_lo, first);
-      ctx->launches += 2;
+      ctx->launches += 2;   // (+ one memset node)
       ctx->cur ^= (n & 1);
       first += n;
       done += n;
@@ -738,7 +741,7 @@ void lbm_destroy(lbm_ctx* ctx) {
     if (s.arena) cudaFree(s.arena);
     if (s.mask) cudaFree(s.mask);
     if (s.partials) { cudaFree(s.partials); cudaFree(s.scratch); cudaFree(s.tickets); }
-    if (s.barrier) cudaFree(s.barrier);
+    if (s.progress) cudaFree(s.progress);
     if (s.av_hi) cudaFree(s.av_hi);
     if (s.av_lo) cudaFree(s.av_lo);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
@@ -932,6 +935,7 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "streaming")) ctx->opt_streaming = (int)value;
   else if (!strcmp(key, "persistent")) ctx->opt_persistent = (int)value;
   else if (!strcmp(key, "chunk_steps")) ctx->opt_chunk = (int)value;
+  else if (!strcmp(key, "global_barrier")) ctx->opt_sync = value ? 1 : 0;
   else return fail("unknown option '%s'", key);
   if (sync_all(ctx)) return 1;
   resolve_options(ctx);

@@ -21,8 +21,10 @@ def main():
         p, cells, obstacles = lbm.decks.load_deck(*lbm.decks.deck_paths(name))
         gold = helpers.golden_av_vels(name)
         for var in args.variants.split(","):
-            pv, vv, tv = var.split(":")
+            pv, vv, tv = var.split(":")[:3]
             opts = {"persistent": int(pv[1:]), "cells_per_thread": int(vv[1:]), "threads_per_block": int(tv[1:])}
+            if len(var.split(":")) > 3:
+                opts["global_barrier"] = int(var.split(":")[3][1:])
             with lbm.cabi.Simulation(p, options=opts) as sim:
                 sim.upload(cells, obstacles)
                 sim.run(min(1000, p.maxIters))      # warm-up
