@@ -323,12 +323,16 @@ def run_b200_arm(args):
     if world > 1:
         sim.halo_push()
         barrier()
+    t_up = time.perf_counter()
     sim.run(args.steps)
     sim.sync()
+    t_loop = time.perf_counter()
     sim.download_cells(out_h)
     hi2, lo2 = sim.download_av_sums(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_parts = {"upload_s": round(t_up - t0, 4), "loop_s": round(t_loop - t_up, 4),
+                 "download_s": round(time.perf_counter() - t_loop, 4)}
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -374,7 +378,9 @@ def run_b200_arm(args):
                         "(includes 1 accelerate pre-pass and the av_vels finalize launches)",
             },
             "e2e": {"value": round(e2e_mlups, 1), "unit": "MLUPS", "h2d_bytes_per_step": h2d // args.steps,
-                    "d2h_bytes_per_step": d2h // args.steps, "seconds": round(e2e_s, 4)},
+                    "d2h_bytes_per_step": d2h // args.steps, "seconds": round(e2e_s, 4), **e2e_parts,
+                    "note": "one upload and one download per run as in the reference (d2q9-bgk.c:196-263), so the "
+                            "bytes per step are the run's bytes / steps; PCIe-bound for short runs"},
             "gpu_launches": launches,
             "clocks": clocks,
             "av_vels_last": float(av[-1]),
