@@ -55,7 +55,7 @@ typedef struct lbm_info {
   int pitch;             /* device row pitch in floats */
   int cells_per_thread;  /* 1, 2 or 4 */
   int threads_per_block;
-  int streaming;         /* cache-hint mode of the lattice loads/stores, 0..4 (lbm_kernels.cuh) */
+  int streaming;         /* cache-hint mode of the lattice loads/stores (lbm_kernels.cuh) */
   int steps_per_launch;  /* 1: one kernel per step; >1: persistent multi-step kernel */
   long long steps_done;
   long long kernel_launches; /* launches of this library's kernels since creation */
@@ -154,8 +154,8 @@ int lbm_run_timed(lbm_ctx *ctx, int nsteps, float *ms);
 /* ---- misc ----------------------------------------------------------------- */
 
 /* Tuning knobs, before lbm_upload: "cells_per_thread" (0 = auto, 1, 2, 4),
- * "threads_per_block", "streaming" (-1 auto, or cache-hint mode 0..4), "persistent" (-1 auto, 0, 1),
- * "chunk_steps".  Unknown key -> non-zero. */
+ * "threads_per_block", "threads_per_sm" (register bound: 512, 768, 1024), "streaming" (0: default
+ * caching, 1: .cs hints), "persistent" (-1 auto, 0, 1), "global_barrier", "chunk_steps".  Unknown key -> non-zero. */
 int lbm_set_option(lbm_ctx *ctx, const char *key, long value);
 int lbm_get_info(lbm_ctx *ctx, lbm_info *info);
 /* Debug canary: number of non-zero floats in the pad columns [nx, pitch) of every row of both

@@ -124,9 +124,9 @@ struct lbm_ctx {
   long long steps_since_upload = 0;
   long long launches = 0;
   // options
-  int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0;
+  int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1;
   // resolved
-  int V = 1, tpb = 256, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
+  int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
   long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
   float w1 = 0.f, w2 = 0.f;
 };
@@ -179,7 +179,9 @@ void resolve_options(lbm_ctx* ctx) {
   ctx->tpb = tpb;
   ctx->segs = (nx + 32 * V - 1) / (32 * V);
   // cache-hint mode of the lattice accesses (lbm_kernels.cuh); plain ld.global.nc / st.global measured best
-  ctx->streaming = (ctx->opt_streaming >= 0 && ctx->opt_streaming <= 4) ? ctx->opt_streaming : 0;
+  ctx->streaming = (ctx->opt_streaming == 1) ? 1 : 0;
+  ctx->tps = (ctx->opt_tps == 768) ? 768 : 1024;
+  ctx->packed = (ctx->V > 1) && (ctx->opt_packed >= 0 ? ctx->opt_packed != 0 : 0);
   long long per_step = 0;
   const int wpb = tpb / 32;
   for (auto& s : ctx->slabs) {
@@ -330,41 +332,53 @@ int create_common(lbm_ctx** out, const lbm_params* p, int nslabs, const int* dev
   return 0;
 }
 
-template <int V, int HINT, int TPB>
+struct Variant {
+  int V, hint, tpb, tps, packed;
+};
+
+template <int V, int HINT, int TPB, int TPS, bool PACKED>
 void launch_step_t(const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
-  lbm::step_kernel<V, HINT, TPB><<<(unsigned)blocks, TPB, 0, st>>>(a);
+  lbm::step_kernel<V, HINT, TPB, TPS, PACKED><<<(unsigned)blocks, TPB, 0, st>>>(a);
+}
+
+template <int V, int HINT, int TPB, int TPS>
+void launch_step_p(const Variant& v, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  if constexpr (V > 1) {
+    if (v.packed) return launch_step_t<V, HINT, TPB, TPS, true>(a, blocks, st);
+  }
+  launch_step_t<V, HINT, TPB, TPS, false>(a, blocks, st);
+}
+
+template <int V, int HINT, int TPB>
+void launch_step_s(const Variant& v, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  if (v.tps == 768 && TPB != 512) launch_step_p<V, HINT, TPB, 768>(v, a, blocks, st);
+  else launch_step_p<V, HINT, TPB, 1024>(v, a, blocks, st);
 }
 
 template <int V, int HINT>
-void launch_step_v(int tpb, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
-  if (tpb == 128) launch_step_t<V, HINT, 128>(a, blocks, st);
-  else if (tpb == 512) launch_step_t<V, HINT, 512>(a, blocks, st);
-  else launch_step_t<V, HINT, 256>(a, blocks, st);
+void launch_step_v(const Variant& v, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  if (v.tpb == 128) launch_step_s<V, HINT, 128>(v, a, blocks, st);
+  else if (v.tpb == 512) launch_step_s<V, HINT, 512>(v, a, blocks, st);
+  else launch_step_s<V, HINT, 256>(v, a, blocks, st);
 }
 
 template <int HINT>
-void launch_step_h(int V, int tpb, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
-  if (V == 4) launch_step_v<4, HINT>(tpb, a, blocks, st);
-  else if (V == 2) launch_step_v<2, HINT>(tpb, a, blocks, st);
-  else launch_step_v<1, HINT>(tpb, a, blocks, st);
+void launch_step_h(const Variant& v, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  if (v.V == 4) launch_step_v<4, HINT>(v, a, blocks, st);
+  else if (v.V == 2) launch_step_v<2, HINT>(v, a, blocks, st);
+  else launch_step_v<1, HINT>(v, a, blocks, st);
 }
 
-void launch_step(int V, int hint, int tpb, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
-  switch (hint) {
-    case 1: launch_step_h<1>(V, tpb, a, blocks, st); break;
-    case 2: launch_step_h<2>(V, tpb, a, blocks, st); break;
-    case 3: launch_step_h<3>(V, tpb, a, blocks, st); break;
-    case 4: launch_step_h<4>(V, tpb, a, blocks, st); break;
-    default: launch_step_h<0>(V, tpb, a, blocks, st); break;
-  }
+void launch_step(const Variant& v, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
+  if (v.hint == 1) launch_step_h<1>(v, a, blocks, st);
+  else launch_step_h<0>(v, a, blocks, st);
 }
 
-
-template <int V, int TPB>
+template <int V, int TPB, bool PACKED>
 int persistent_grid_t(int device, int rows, long long* grid, int* rows_per_block) {
   // block b owns rows [b*rpb, (b+1)*rpb): as many blocks as can be co-resident (cooperative launch)
   int per_sm = 0, sms = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::persistent_kernel<V, TPB>, TPB, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::persistent_kernel<V, TPB, PACKED>, TPB, 0));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const long long resident = std::max(1LL, (long long)per_sm * sms);
   const int rpb = (int)std::max(1LL, (rows + resident - 1) / resident);
@@ -373,40 +387,50 @@ int persistent_grid_t(int device, int rows, long long* grid, int* rows_per_block
   return 0;
 }
 
-template <int V, int TPB>
+template <int V, int TPB, bool PACKED>
 int launch_persistent_t(const lbm::PersistArgs& pa, long long grid, cudaStream_t st) {
   void* args[] = {const_cast<lbm::PersistArgs*>(&pa)};
-  CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lbm::persistent_kernel<V, TPB>), dim3((unsigned)grid),
+  CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lbm::persistent_kernel<V, TPB, PACKED>), dim3((unsigned)grid),
                                  dim3(TPB), args, 0, st));
   return 0;
 }
 
-#define LBM_DISPATCH_V_TPB(V_, TPB_, CALL)                                  \
+#define LBM_DISPATCH_V_TPB(V_, TPB_, P_, CALL)                              \
   do {                                                                      \
     if ((V_) == 4) {                                                        \
-      if ((TPB_) == 128) return CALL(4, 128);                               \
-      if ((TPB_) == 512) return CALL(4, 512);                               \
-      return CALL(4, 256);                                                  \
+      if (P_) {                                                             \
+        if ((TPB_) == 128) return CALL(4, 128, true);                       \
+        if ((TPB_) == 512) return CALL(4, 512, true);                       \
+        return CALL(4, 256, true);                                          \
+      }                                                                     \
+      if ((TPB_) == 128) return CALL(4, 128, false);                        \
+      if ((TPB_) == 512) return CALL(4, 512, false);                        \
+      return CALL(4, 256, false);                                           \
     } else if ((V_) == 2) {                                                 \
-      if ((TPB_) == 128) return CALL(2, 128);                               \
-      if ((TPB_) == 512) return CALL(2, 512);                               \
-      return CALL(2, 256);                                                  \
+      if (P_) {                                                             \
+        if ((TPB_) == 128) return CALL(2, 128, true);                       \
+        if ((TPB_) == 512) return CALL(2, 512, true);                       \
+        return CALL(2, 256, true);                                          \
+      }                                                                     \
+      if ((TPB_) == 128) return CALL(2, 128, false);                        \
+      if ((TPB_) == 512) return CALL(2, 512, false);                        \
+      return CALL(2, 256, false);                                           \
     } else {                                                                \
-      if ((TPB_) == 128) return CALL(1, 128);                               \
-      if ((TPB_) == 512) return CALL(1, 512);                               \
-      return CALL(1, 256);                                                  \
+      if ((TPB_) == 128) return CALL(1, 128, false);                        \
+      if ((TPB_) == 512) return CALL(1, 512, false);                        \
+      return CALL(1, 256, false);                                           \
     }                                                                       \
   } while (0)
 
-int persistent_grid(int V, int tpb, int device, int rows, long long* grid, int* rows_per_block) {
-#define CALL_(v, t) persistent_grid_t<v, t>(device, rows, grid, rows_per_block)
-  LBM_DISPATCH_V_TPB(V, tpb, CALL_);
+int persistent_grid(const Variant& v, int device, int rows, long long* grid, int* rows_per_block) {
+#define CALL_(vv, t, p) persistent_grid_t<vv, t, p>(device, rows, grid, rows_per_block)
+  LBM_DISPATCH_V_TPB(v.V, v.tpb, v.packed, CALL_);
 #undef CALL_
 }
 
-int launch_persistent(int V, int tpb, const lbm::PersistArgs& pa, long long grid, cudaStream_t st) {
-#define CALL_(v, t) launch_persistent_t<v, t>(pa, grid, st)
-  LBM_DISPATCH_V_TPB(V, tpb, CALL_);
+int launch_persistent(const Variant& v, const lbm::PersistArgs& pa, long long grid, cudaStream_t st) {
+#define CALL_(vv, t, p) launch_persistent_t<vv, t, p>(pa, grid, st)
+  LBM_DISPATCH_V_TPB(v.V, v.tpb, v.packed, CALL_);
 #undef CALL_
 }
 
@@ -466,7 +490,8 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
     // one cooperative launch per chunk of steps; grid barrier between steps (lbm_kernels.cuh)
     Slab& s = ctx->slabs[0];
     if (set_device(s)) return 1;
-    if (persistent_grid(ctx->V, ctx->tpb, s.device, s.rows, &s.pblocks, &s.rows_per_block)) return 1;
+    const Variant var{ctx->V, ctx->streaming, ctx->tpb, ctx->tps, ctx->packed};
+    if (persistent_grid(var, s.device, s.rows, &s.pblocks, &s.rows_per_block)) return 1;
     if (s.progress_capacity < s.pblocks) {
       if (s.progress) CK(cudaFree(s.progress));
       CK(cudaMalloc(&s.progress, sizeof(unsigned int) * 32 * (size_t)s.pblocks));
@@ -507,7 +532,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
       pa.partials = s.partials;
       pa.global_barrier = ctx->opt_sync;
       CK(cudaMemsetAsync(s.progress, 0, sizeof(unsigned int) * 32 * (size_t)s.pblocks, s.stream));
-      if (launch_persistent(ctx->V, ctx->tpb, pa, s.pblocks, s.stream)) return 1;
+      if (launch_persistent(var, pa, s.pblocks, s.stream)) return 1;
       lbm::av_finalize_kernel<<<dim3(1, n), 256, 0, s.stream>>>(s.partials, s.pblocks, s.scratch, s.tickets, s.av_hi,
                                                                  s.av_lo, first);
       ctx->launches += 2;   // (+ one memset node)
@@ -554,7 +579,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         a.edge_target = s.step_launches * (unsigned long long)ctx->segs;
       }
       a.epoch = ctx->epoch;
-      launch_step(ctx->V, ctx->streaming, ctx->tpb, a, s.blocks, s.stream);
+      launch_step(Variant{ctx->V, ctx->streaming, ctx->tpb, ctx->tps, ctx->packed}, a, s.blocks, s.stream);
       ctx->launches++;
     }
     ctx->cur ^= 1;
@@ -936,6 +961,8 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "persistent")) ctx->opt_persistent = (int)value;
   else if (!strcmp(key, "chunk_steps")) ctx->opt_chunk = (int)value;
   else if (!strcmp(key, "global_barrier")) ctx->opt_sync = value ? 1 : 0;
+  else if (!strcmp(key, "threads_per_sm")) ctx->opt_tps = (int)value;
+  else if (!strcmp(key, "packed")) ctx->opt_packed = (int)value;
   else return fail("unknown option '%s'", key);
   if (sync_all(ctx)) return 1;
   resolve_options(ctx);
@@ -989,10 +1016,11 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
   info->kernel_launches = ctx->launches;
   info->partials_per_step = ctx->per_step;
   if (ctx->persistent)
-    snprintf(info->kernel_name, sizeof info->kernel_name, "persistent_kernel<V=%d,tpb=%d>", ctx->V, ctx->tpb);
+    snprintf(info->kernel_name, sizeof info->kernel_name, "persistent_kernel<V=%d,tpb=%d,packed=%d>", ctx->V, ctx->tpb,
+             ctx->packed);
   else
-    snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d>", ctx->V,
-             ctx->streaming, ctx->tpb);
+    snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d,tps=%d,packed=%d>", ctx->V,
+             ctx->streaming, ctx->tpb, ctx->tps, ctx->packed);
   return 0;
 }
 

@@ -2,9 +2,18 @@
  * oracle/lbm_oracle.c — CPU restatement of the reference's D2Q9-BGK time step.
  *
  * TEST INFRASTRUCTURE ONLY (see lbm_oracle.h).  Plain C99, IEEE arithmetic,
- * built with -ffp-contract=off so that every fp32 operation below is one
- * correctly rounded add / mul / div / sqrt in exactly the order written; the
- * CUDA path is required to reproduce the resulting lattice bit for bit.
+ * built with -ffp-contract=off so that every fp32 operation below is exactly
+ * the correctly rounded add / mul / fma / div / sqrt written, in the order
+ * written; the CUDA path is required to reproduce the resulting lattice bit
+ * for bit.
+ *
+ * Contraction: OpenCL C contracts a*b+c into a fused multiply-add by default
+ * (FP_CONTRACT is ON; the reference even adds -cl-fast-relaxed-math for
+ * 128x128, d2q9-bgk.c:642-645, and calls mad() itself, kernels.cl:36-42), so
+ * the collision below states the contraction explicitly: every product of
+ * kernels.cl:143-197 that feeds an addition is one fmaf().  Nothing is left to
+ * a compiler's discretion on either side (gcc: -ffp-contract=off; nvcc:
+ * explicitly rounded intrinsics).
  *
  * Citations are file:line in the reference tree (ag14774/OpenCL-Lattice-Boltzmann).
  *
@@ -12,7 +21,8 @@
  *   native_recip(x) -> 1.0f / x          (kernels.cl:129)
  *   native_sqrt(x)  -> sqrtf(x)          (kernels.cl:198)
  *   native_divide   -> /                 (kernels.cl:14-15)
- *   mad(a, b, c)    -> a * b + c, unfused (kernels.cl:36-42)
+ *   mad(mask, w, c) -> mask * w + c       (kernels.cl:36-42; mask is 0 or 1, so the
+ *                                          product is exact and fusing changes nothing)
  */
 #include "lbm_oracle.h"
 
@@ -86,36 +96,39 @@ static inline float collide_f32(const float t[NSPEEDS], int lmask, float omega, 
   u_y -= t[7];
   u_y -= t[8];
 
-  float u_sq = u_x * u_x + u_y * u_y;             /* kernels.cl:143 */
+  float u_sq = fmaf(u_x, u_x, u_y * u_y);         /* kernels.cl:143, contracted */
 
-  /* kernels.cl:146-154 */
+  /* kernels.cl:146-154; uvec[3,4,7,8] are the negatives of uvec[1,2,5,6] */
   float uvec[NSPEEDS];
   uvec[1] = u_x;
   uvec[2] = u_y;
-  uvec[3] = -u_x;
-  uvec[4] = -u_y;
   uvec[5] = u_x + u_y;
   uvec[6] = -u_x + u_y;
-  uvec[7] = -u_x - u_y;
-  uvec[8] = u_x - u_y;
 
-  /* kernels.cl:156-174 */
-  float icu[NSPEEDS], icu_sq[NSPEEDS];
-  for (int k = 1; k < NSPEEDS; k++) {
-    icu[k] = uvec[k] * ic_sq;
-    icu_sq[k] = icu[k] * uvec[k];
-  }
-
-  /* kernels.cl:176-185; `0.5f * densinv*ic_sq * x` groups as ((0.5f*densinv)*ic_sq)*x */
+  /* kernels.cl:176-185: `0.5f * densinv*ic_sq` groups as ((0.5f*densinv)*ic_sq) */
   const float half_inv = 0.5f * densinv * ic_sq;
-  float d_equ[NSPEEDS];
-  d_equ[0] = w0 * (densvec - half_inv * u_sq);
-  for (int k = 1; k <= 4; k++) d_equ[k] = w1 * (densvec + icu[k] + half_inv * (icu_sq[k] - u_sq));
-  for (int k = 5; k <= 8; k++) d_equ[k] = w2 * (densvec + icu[k] + half_inv * (icu_sq[k] - u_sq));
+  const float relax = (float)lmask * omega;       /* kernels.cl:187-197: lmask*OMEGA */
+  static const int plus[4] = {1, 2, 5, 6}, minus[4] = {3, 4, 7, 8};
 
-  /* kernels.cl:187-197; `lmask*OMEGA*(d - t)` groups as ((float)lmask*OMEGA)*(d - t) */
-  const float relax = (float)lmask * omega;
-  for (int k = 0; k < NSPEEDS; k++) v[k] = t[k] + relax * (d_equ[k] - t[k]);
+  /* d_equ[0] = w0 * (densvec - half_inv*u_sq); v[0] = t[0] + relax*(d_equ[0] - t[0]) */
+  {
+    const float y = fmaf(-half_inv, u_sq, densvec);
+    const float r = fmaf(w0, y, -t[0]);
+    v[0] = fmaf(relax, r, t[0]);
+  }
+  for (int i = 0; i < 4; i++) {
+    const int kp = plus[i], km = minus[i];
+    const float w = (i < 2) ? w1 : w2;
+    const float u = uvec[kp];
+    /* ic_sqtimesu = u*ic_sq (kernels.cl:156-164); ic_sqtimesu_sq - u_sq = (u*ic_sq)*u - u_sq (:166-185) */
+    const float s = fmaf(u * ic_sq, u, -u_sq);
+    /* d_equ[k] = w * (densvec + ic_sqtimesu[k] + half_inv * s), for +u and for -u */
+    const float yp = fmaf(half_inv, s, fmaf(u, ic_sq, densvec));
+    const float ym = fmaf(half_inv, s, fmaf(u, -ic_sq, densvec));
+    /* v[k] = t[k] + relax * (d_equ[k] - t[k]) */
+    v[kp] = fmaf(relax, fmaf(w, yp, -t[kp]), t[kp]);
+    v[km] = fmaf(relax, fmaf(w, ym, -t[km]), t[km]);
+  }
 
   return (float)lmask * sqrtf(u_sq) * densinv;    /* kernels.cl:198 */
 }

@@ -10,7 +10,8 @@
  * reference ships for this path (check/128x128.*, check/128x256.*,
  * check/256x256.av_vels.dat, check/1024x1024.av_vels.dat) — see
  * tests/test_oracle_goldens.py; the fp32 variant (the arithmetic of
- * kernels.cl) passes the reference checker's 1 % gate against the same files.
+ * kernels.cl, multiply-adds contracted explicitly as OpenCL does by default)
+ * passes the reference checker's 1 % gate against the same files.
  *
  * Data layout is the reference's (d2q9-bgk.c:73): SoA, nine planes of ny*nx
  * values, index sp*nx*ny + ii*nx + jj, ii = row (y), jj = column (x).

@@ -23,8 +23,9 @@ def main():
         for var in args.variants.split(","):
             pv, vv, tv = var.split(":")[:3]
             opts = {"persistent": int(pv[1:]), "cells_per_thread": int(vv[1:]), "threads_per_block": int(tv[1:])}
-            if len(var.split(":")) > 3:
-                opts["global_barrier"] = int(var.split(":")[3][1:])
+            for extra in var.split(":")[3:]:
+                key = {"g": "global_barrier", "k": "packed", "s": "threads_per_sm"}[extra[0]]
+                opts[key] = int(extra[1:])
             with lbm.cabi.Simulation(p, options=opts) as sim:
                 sim.upload(cells, obstacles)
                 sim.run(min(1000, p.maxIters))      # warm-up

@@ -92,8 +92,9 @@ def main():
     kname = data[0][hdr.index("Kernel Name")]
     # "void step_kernel<4, 1, 256>(StepArgs)" -> bench.py's info name
     import re
-    m = re.search(r"step_kernel<(\d+), (\d+), (\d+)>", kname)
-    name = f"step_kernel<V={m.group(1)},hint={m.group(2)},tpb={m.group(3)}>" if m else kname
+    m = re.search(r"step_kernel<(\d+), (\d+), (\d+), (\d+), (\d+)>", kname)
+    name = (f"step_kernel<V={m.group(1)},hint={m.group(2)},tpb={m.group(3)},tps={m.group(4)},packed={m.group(5)}>"
+            if m else kname)
     rec = {"kernel": name, "ncu_kernel_name": kname, "cells_per_launch": cells,
            "dram_bytes_read_per_launch": sum(rd) / len(rd), "dram_bytes_write_per_launch": sum(wr) / len(wr),
            "dram_bytes_per_launch": per_launch, "algorithmic_bytes_per_launch": 72 * cells,

@@ -36,6 +36,8 @@ def main():
         parts = [int(x) for x in var.split(":")]
         V, tpb, st = parts[:3]
         sim.set_option("persistent", parts[3] if len(parts) > 3 else 0)
+        sim.set_option("threads_per_sm", parts[4] if len(parts) > 4 else 1024)
+        sim.set_option("packed", parts[5] if len(parts) > 5 else 0)
         sim.set_option("cells_per_thread", V)
         sim.set_option("threads_per_block", tpb)
         sim.set_option("streaming", st)
@@ -43,7 +45,7 @@ def main():
         sim.sync()
         ms = sim.run_timed(args.steps)
         mlups = args.nx * args.ny * args.steps / (ms * 1e-3) / 1e6
-        print(f"{sim.info()['kernel_name']} V={V} tpb={tpb} hint={st}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
+        print(f"{sim.info()['kernel_name']} V={V} tpb={tpb} hint={st} tps={parts[4] if len(parts) > 4 else 1024}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
               f"{mlups*72/1e3:,.0f} GB/s  {mlups*72/1e3/peak*100:.1f}% of measured HBM copy", flush=True)
     print(sim.info())
     sim.close()
