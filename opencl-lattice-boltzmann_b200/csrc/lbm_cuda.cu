@@ -43,11 +43,15 @@ int fail(const char* fmt, ...) {
 constexpr unsigned long long BLOB_MAGIC = 0x4c424d4232303031ULL;  // "LBMB2001"
 
 // Geometry of one slab's lattice arena, enough for a neighbour to address its
-// ghost rows and flags: [buffer 0 | buffer 1 | flags].
+// ghost rows, flags and obstacle mask: [buffer 0 | buffer 1 | flags | mask].
+// Every plane has GHOST ghost rows below row 0 and GHOST above row rows-1; the
+// mask has one ghost row on each side.
+constexpr int GHOST = 2;
 struct ArenaLayout {
-  long long plane_stride;  // floats
+  long long plane_stride;  // floats = (rows + 2*GHOST) * pitch
   long long buf_floats;    // 9 * plane_stride
   long long flags_offset;  // bytes from arena base
+  long long mask_offset;   // bytes from arena base to mask ghost row -1
   int rows;
   int pitch;
 };
@@ -72,7 +76,7 @@ struct Slab {
   cudaStream_t stream = nullptr;
   float* arena = nullptr;
   ArenaLayout layout{};
-  uint32_t* mask = nullptr;
+  uint32_t* mask = nullptr;      // row 0 of the obstacle bit mask (inside the arena; ghost rows -1 and rows)
   double2* partials = nullptr;   // chunk_steps x blocks_per_step block partials
   double2* scratch = nullptr;    // chunk_steps x splits range sums of av_finalize_kernel
   unsigned int* tickets = nullptr;
@@ -90,17 +94,23 @@ struct Slab {
   unsigned long long step_launches = 0;  // step kernels launched on this slab (for edge_target)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 
-  float* row0(int buf) const { return arena + (long long)buf * layout.buf_floats + layout.pitch; }
+  float* row0(int buf) const { return arena + (long long)buf * layout.buf_floats + (long long)GHOST * layout.pitch; }
   unsigned long long* flags() const {
     return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(arena) + layout.flags_offset);
   }
 };
 
-float* nb_ghost_below(const Neighbour& n, int buf) {  // its ghost row -1
-  return n.arena + (long long)buf * n.layout.buf_floats;
+float* nb_ghost_below(const Neighbour& n, int buf) {  // its ghost row -1 (row -2 is one pitch lower)
+  return n.arena + (long long)buf * n.layout.buf_floats + (long long)(GHOST - 1) * n.layout.pitch;
 }
-float* nb_ghost_above(const Neighbour& n, int buf) {  // its ghost row `rows`
-  return n.arena + (long long)buf * n.layout.buf_floats + (long long)(n.layout.rows + 1) * n.layout.pitch;
+float* nb_ghost_above(const Neighbour& n, int buf) {  // its ghost row `rows` (row rows+1 is one pitch higher)
+  return n.arena + (long long)buf * n.layout.buf_floats + (long long)(n.layout.rows + GHOST) * n.layout.pitch;
+}
+uint32_t* nb_mask_ghost_below(const Neighbour& n) {   // its mask ghost row -1
+  return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(n.arena) + n.layout.mask_offset);
+}
+uint32_t* nb_mask_ghost_above(const Neighbour& n) {   // its mask ghost row `rows`
+  return nb_mask_ghost_below(n) + (long long)(n.layout.rows + 1) * (n.layout.pitch / 32);
 }
 unsigned long long* nb_flags(const Neighbour& n) {
   return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(n.arena) + n.layout.flags_offset);
@@ -160,7 +170,7 @@ int validate(const lbm_params* p) {
 void resolve_options(lbm_ctx* ctx) {
   const int nx = ctx->p.nx;
   // L2-resident single-slab lattices run many steps per (cooperative) launch
-  const double lattice_bytes = 2.0 * 9.0 * 4.0 * (double)ctx->pitch * (double)(ctx->rows + 2);
+  const double lattice_bytes = 2.0 * 9.0 * 4.0 * (double)ctx->pitch * (double)(ctx->rows + 2 * GHOST);
   const bool can_persist = ctx->slabs.size() == 1 && ctx->nranks == 1;
   ctx->persistent = can_persist && (ctx->opt_persistent >= 0 ? ctx->opt_persistent != 0
                                                               : lattice_bytes <= 96.0 * 1024 * 1024);
@@ -199,16 +209,17 @@ int alloc_slab(lbm_ctx* ctx, Slab& s) {
   const int pitch = ctx->pitch;
   s.layout.pitch = pitch;
   s.layout.rows = s.rows;
-  s.layout.plane_stride = (long long)(s.rows + 2) * pitch;
+  s.layout.plane_stride = (long long)(s.rows + 2 * GHOST) * pitch;
   s.layout.buf_floats = 9 * s.layout.plane_stride;
   s.layout.flags_offset = 2 * s.layout.buf_floats * (long long)sizeof(float);
-  const size_t arena_bytes = (size_t)s.layout.flags_offset + 256;
+  s.layout.mask_offset = s.layout.flags_offset + 256;
+  const size_t mask_bytes = sizeof(uint32_t) * (size_t)ctx->mask_pitch * (size_t)(s.rows + 2);
+  const size_t arena_bytes = (size_t)s.layout.mask_offset + mask_bytes;
   // stream-ordered clears: a plain cudaMemset runs on the legacy stream, which the slab's
   // non-blocking stream does not wait for, and could still be clearing when lbm_upload copies
   CK(cudaMalloc(&s.arena, arena_bytes));
   CK(cudaMemsetAsync(s.arena, 0, arena_bytes, s.stream));
-  CK(cudaMalloc(&s.mask, sizeof(uint32_t) * (size_t)ctx->mask_pitch * s.rows));
-  CK(cudaMemsetAsync(s.mask, 0, sizeof(uint32_t) * (size_t)ctx->mask_pitch * s.rows, s.stream));
+  s.mask = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s.arena) + s.layout.mask_offset) + ctx->mask_pitch;
   CK(cudaStreamSynchronize(s.stream));
   CK(cudaEventCreate(&s.ev_start));
   CK(cudaEventCreate(&s.ev_stop));
@@ -576,7 +587,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         a.peer_up_flag = nb_flags(s.up) + 1;
         a.peer_down_flag = nb_flags(s.down) + 0;
         s.step_launches++;
-        a.edge_target = s.step_launches * (unsigned long long)ctx->segs;
+        a.edge_target = s.step_launches * (unsigned long long)ctx->segs * (unsigned long long)std::min(GHOST, s.rows);
       }
       a.epoch = ctx->epoch;
       launch_step(Variant{ctx->V, ctx->streaming, ctx->tpb, ctx->tps, ctx->packed}, a, s.blocks, s.stream);
@@ -626,17 +637,27 @@ int sync_all(lbm_ctx* ctx) {
 }
 
 int push_halos(lbm_ctx* ctx) {
-  // Every slab copies its top row (all nine planes) into the up neighbour's ghost
-  // row below, and its bottom row into the down neighbour's ghost row above.
+  // Every slab copies its top GHOST rows (all nine planes) into the up neighbour's ghost rows
+  // below, its bottom GHOST rows into the down neighbour's ghost rows above, and the matching
+  // obstacle-mask rows (one each way).
   const size_t width = sizeof(float) * (size_t)ctx->p.nx;
+  const size_t mwidth = sizeof(uint32_t) * (size_t)ctx->mask_pitch;
   for (auto& s : ctx->slabs) {
     if (set_device(s)) return 1;
-    const float* top = s.row0(ctx->cur) + (long long)(s.rows - 1) * ctx->pitch;
-    const float* bot = s.row0(ctx->cur);
-    CK(cudaMemcpy2DAsync(nb_ghost_below(s.up, ctx->cur), sizeof(float) * s.up.layout.plane_stride, top,
-                         sizeof(float) * s.layout.plane_stride, width, 9, cudaMemcpyDefault, s.stream));
-    CK(cudaMemcpy2DAsync(nb_ghost_above(s.down, ctx->cur), sizeof(float) * s.down.layout.plane_stride, bot,
-                         sizeof(float) * s.layout.plane_stride, width, 9, cudaMemcpyDefault, s.stream));
+    for (int d = 1; d <= GHOST && d <= s.rows; d++) {
+      // my row rows-d -> the up neighbour's ghost row -d; my row d-1 -> the down neighbour's ghost row rows+d-1
+      const float* top = s.row0(ctx->cur) + (long long)(s.rows - d) * ctx->pitch;
+      const float* bot = s.row0(ctx->cur) + (long long)(d - 1) * ctx->pitch;
+      float* up = nb_ghost_below(s.up, ctx->cur) - (long long)(d - 1) * ctx->pitch;
+      float* down = nb_ghost_above(s.down, ctx->cur) + (long long)(d - 1) * ctx->pitch;
+      CK(cudaMemcpy2DAsync(up, sizeof(float) * s.up.layout.plane_stride, top, sizeof(float) * s.layout.plane_stride,
+                           width, 9, cudaMemcpyDefault, s.stream));
+      CK(cudaMemcpy2DAsync(down, sizeof(float) * s.down.layout.plane_stride, bot, sizeof(float) * s.layout.plane_stride,
+                           width, 9, cudaMemcpyDefault, s.stream));
+    }
+    CK(cudaMemcpyAsync(nb_mask_ghost_below(s.up), s.mask + (size_t)(s.rows - 1) * ctx->mask_pitch, mwidth,
+                       cudaMemcpyDefault, s.stream));
+    CK(cudaMemcpyAsync(nb_mask_ghost_above(s.down), s.mask, mwidth, cudaMemcpyDefault, s.stream));
   }
   return sync_all(ctx);
 }
@@ -764,7 +785,6 @@ void lbm_destroy(lbm_ctx* ctx) {
     if (s.up.ipc && s.up.arena) cudaIpcCloseMemHandle(s.up.arena);
     if (s.down.ipc && s.down.arena) cudaIpcCloseMemHandle(s.down.arena);
     if (s.arena) cudaFree(s.arena);
-    if (s.mask) cudaFree(s.mask);
     if (s.partials) { cudaFree(s.partials); cudaFree(s.scratch); cudaFree(s.tickets); }
     if (s.progress) cudaFree(s.progress);
     if (s.av_hi) cudaFree(s.av_hi);
@@ -988,7 +1008,7 @@ int lbm_debug_pad_nonzero(lbm_ctx* ctx, long long* count) {
   if (sync_all(ctx)) return 1;
   for (auto& s : ctx->slabs) {
     if (set_device(s)) return 1;
-    const size_t nrows = (size_t)2 * 9 * (s.rows + 2);
+    const size_t nrows = (size_t)2 * 9 * (s.rows + 2 * GHOST);
     std::vector<float> host(nrows * pad);
     CK(cudaMemcpy2D(host.data(), sizeof(float) * pad, s.arena + ctx->p.nx, sizeof(float) * ctx->pitch,
                     sizeof(float) * pad, nrows, cudaMemcpyDeviceToHost));
