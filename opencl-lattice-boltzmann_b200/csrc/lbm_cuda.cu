@@ -8,6 +8,7 @@
 // (the reference bakes 6-decimal -D constants into a run-time build, :643-645).
 #include "lbm.h"
 #include "lbm_kernels.cuh"
+#include "lbm_fuse2.cuh"
 
 #include <cuda_runtime.h>
 
@@ -91,7 +92,9 @@ struct Slab {
   double* av_lo = nullptr;
   long long av_capacity = 0;
   Neighbour up, down;
-  unsigned long long step_launches = 0;  // step kernels launched on this slab (for edge_target)
+  unsigned long long edge_expected = 0;  // edge-row completions counted so far on this slab (edge_target of the next launch)
+  int f2_strips = 1, f2_segs_y = 1;      // tiling of the two-step kernel
+  long long pstride = 0;                 // partial entries per step = max(step-kernel blocks, two-step blocks)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 
   float* row0(int buf) const { return arena + (long long)buf * layout.buf_floats + (long long)GHOST * layout.pitch; }
@@ -134,8 +137,10 @@ struct lbm_ctx {
   long long steps_since_upload = 0;
   long long launches = 0;
   // options
-  int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1;
+  int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0;
   // resolved
+  int fuse2 = 0, f2_warps = 4, f2_rows = 256;
   int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
   long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
   float w1 = 0.f, w2 = 0.f;
@@ -202,6 +207,24 @@ void resolve_options(lbm_ctx* ctx) {
   ctx->per_step = per_step;
   long long chunk = ctx->opt_chunk > 0 ? ctx->opt_chunk : (64LL << 20) / (16 * std::max(1LL, per_step));
   ctx->chunk_steps = (int)std::max(1LL, std::min(chunk, 4096LL));
+
+  // two time steps per HBM pass (lbm_fuse2.cuh): 128-bit kernel only, lattices streamed from HBM,
+  // every slab of the ring at least 4 rows (an even split, so every rank decides alike)
+  ctx->f2_warps = (ctx->opt_f2_warps == 2 || ctx->opt_f2_warps == 4 || ctx->opt_f2_warps == 8) ? ctx->opt_f2_warps : 4;
+  ctx->f2_rows = ctx->opt_f2_rows >= 4 ? ctx->opt_f2_rows : 256;
+  const long long total_slabs = (long long)ctx->nranks * (long long)ctx->slabs.size();
+  const bool can_fuse = !ctx->persistent && V == 4 && nx >= 8 && (ctx->p.ny / total_slabs) >= 4;
+  ctx->fuse2 = can_fuse && (ctx->opt_fuse2 >= 0 ? ctx->opt_fuse2 != 0 : 0);
+  if (ctx->fuse2) {
+    ctx->chunk_steps = std::max(2, ctx->chunk_steps);
+    const int tx = 128 * ctx->f2_warps;
+    for (auto& s : ctx->slabs) {
+      s.f2_strips = (nx + tx - 1) / tx;
+      s.f2_segs_y = (s.rows + ctx->f2_rows - 1) / ctx->f2_rows;
+    }
+  }
+  for (auto& s : ctx->slabs)
+    s.pstride = std::max(s.blocks, ctx->fuse2 ? (long long)s.f2_strips * s.f2_segs_y : 0LL);
 }
 
 int alloc_slab(lbm_ctx* ctx, Slab& s) {
@@ -255,7 +278,7 @@ int ensure_partials(lbm_ctx* ctx) {
     if (s.partials) continue;
     if (set_device(s)) return 1;
     // the persistent kernel has at most one block per row, the step kernel s.blocks blocks
-    s.partial_capacity = (long long)ctx->chunk_steps * std::max<long long>(s.blocks, ctx->persistent ? s.rows : 0);
+    s.partial_capacity = (long long)ctx->chunk_steps * std::max<long long>(s.pstride, ctx->persistent ? s.rows : 0);
     CK(cudaMalloc(&s.partials, sizeof(double2) * (size_t)s.partial_capacity));
     CK(cudaMalloc(&s.scratch, sizeof(double2) * (size_t)ctx->chunk_steps * (size_t)s.splits));
     CK(cudaMalloc(&s.tickets, sizeof(unsigned int) * (size_t)ctx->chunk_steps));
@@ -445,6 +468,26 @@ int launch_persistent(const Variant& v, const lbm::PersistArgs& pa, long long gr
 #undef CALL_
 }
 
+template <int W, bool PACKED, int MINB>
+int launch_fuse2_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  static bool configured[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    CK(cudaFuncSetAttribute(lbm::fuse2_kernel<W, PACKED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            lbm::fuse2_smem_bytes<W>()));
+    configured[dev] = true;
+  }
+  lbm::fuse2_kernel<W, PACKED, MINB><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2_smem_bytes<W>(), st>>>(fa);
+  return 0;
+}
+
+int launch_fuse2(int warps, int packed, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  if (warps == 2) return packed ? launch_fuse2_t<2, true, 5>(fa, grid, st) : launch_fuse2_t<2, false, 5>(fa, grid, st);
+  if (warps == 8) return packed ? launch_fuse2_t<8, true, 1>(fa, grid, st) : launch_fuse2_t<8, false, 1>(fa, grid, st);
+  return packed ? launch_fuse2_t<4, true, 3>(fa, grid, st) : launch_fuse2_t<4, false, 3>(fa, grid, st);
+}
+
 // local row of global row ny-2 in this slab, or -1
 int accel_row_of(const lbm_ctx* ctx, const Slab& s) {
   const int g = ctx->p.ny - 2;
@@ -555,9 +598,24 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
 
   int in_chunk = 0;
   long long chunk_first = ctx->steps_since_upload;
-  for (int t = 0; !ctx->persistent && t < nsteps; t++) {
+  auto flush_chunk = [&]() -> int {   // per-step Σ|u| of the chunk's steps -> av_hi/av_lo
+    if (in_chunk == 0) return 0;
+    for (auto& s : ctx->slabs) {
+      if (set_device(s)) return 1;
+      lbm::av_finalize_kernel<<<dim3(s.splits, in_chunk), 256, 0, s.stream>>>(s.partials, s.pstride, s.scratch, s.tickets,
+                                                                               s.av_hi, s.av_lo, chunk_first);
+      ctx->launches++;
+    }
+    chunk_first += in_chunk;
+    in_chunk = 0;
+    return 0;
+  };
+  for (int t = 0; !ctx->persistent && t < nsteps;) {
+    const bool pair = ctx->fuse2 && (nsteps - t >= 2);   // two steps in one launch; an odd tail runs one step
+    const int adv = pair ? 2 : 1;
+    if (in_chunk + adv > ctx->chunk_steps && flush_chunk()) return 1;
     ctx->epoch++;
-    const bool last = (t == nsteps - 1);
+    const bool last = (t + adv == nsteps);
     for (auto& s : ctx->slabs) {
       if (set_device(s)) return 1;
       lbm::StepArgs a{};
@@ -578,7 +636,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
       a.up_plane_stride = s.up.layout.plane_stride;
       a.down_ghost = nb_ghost_above(s.down, ctx->cur ^ 1);
       a.down_plane_stride = s.down.layout.plane_stride;
-      a.partials = s.partials + (long long)in_chunk * s.blocks;
+      a.partials = s.partials + (long long)in_chunk * s.pstride;
       if (ctx->ring) {
         unsigned long long* f = s.flags();
         a.flag_from_up = f + 0;
@@ -586,25 +644,36 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         a.edge_count = f + 2;
         a.peer_up_flag = nb_flags(s.up) + 1;
         a.peer_down_flag = nb_flags(s.down) + 0;
-        s.step_launches++;
-        a.edge_target = s.step_launches * (unsigned long long)ctx->segs * (unsigned long long)std::min(GHOST, s.rows);
+        // completions this launch adds to each edge counter: warps of the two edge rows, or edge blocks
+        s.edge_expected += pair ? (unsigned long long)s.f2_strips
+                                : (unsigned long long)ctx->segs * (unsigned long long)std::min(GHOST, s.rows);
+        a.edge_target = s.edge_expected;
       }
       a.epoch = ctx->epoch;
-      launch_step(Variant{ctx->V, ctx->streaming, ctx->tpb, ctx->tps, ctx->packed}, a, s.blocks, s.stream);
+      if (pair) {
+        lbm::Fuse2Args fa{};
+        fa.s = a;
+        fa.y0 = s.y0;
+        fa.ny = ctx->p.ny;
+        fa.last = last ? 1 : 0;
+        fa.strips = s.f2_strips;
+        fa.segs_y = s.f2_segs_y;
+        fa.seg_rows = ctx->f2_rows;
+        fa.partials1 = s.partials + (long long)in_chunk * s.pstride;
+        fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
+        fa.per_step = s.pstride;
+        if (launch_fuse2(ctx->f2_warps, ctx->packed, fa, (long long)s.f2_strips * s.f2_segs_y, s.stream)) return 1;
+      } else {
+        if (s.pstride > s.blocks)   // (tiny grids only) the step kernel writes s.blocks partials: clear the rest
+          CK(cudaMemsetAsync(a.partials + s.blocks, 0, sizeof(double2) * (size_t)(s.pstride - s.blocks), s.stream));
+        launch_step(Variant{ctx->V, ctx->streaming, ctx->tpb, ctx->tps, ctx->packed}, a, s.blocks, s.stream);
+      }
       ctx->launches++;
     }
     ctx->cur ^= 1;
-    in_chunk++;
-    if (in_chunk == ctx->chunk_steps || last) {
-      for (auto& s : ctx->slabs) {
-        if (set_device(s)) return 1;
-        lbm::av_finalize_kernel<<<dim3(s.splits, in_chunk), 256, 0, s.stream>>>(s.partials, s.blocks, s.scratch, s.tickets,
-                                                                                 s.av_hi, s.av_lo, chunk_first);
-        ctx->launches++;
-      }
-      chunk_first += in_chunk;
-      in_chunk = 0;
-    }
+    in_chunk += adv;
+    t += adv;
+    if ((in_chunk == ctx->chunk_steps || t == nsteps) && flush_chunk()) return 1;
   }
   CK(cudaGetLastError());
   ctx->steps_done += nsteps;
@@ -983,6 +1052,9 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "global_barrier")) ctx->opt_sync = value ? 1 : 0;
   else if (!strcmp(key, "threads_per_sm")) ctx->opt_tps = (int)value;
   else if (!strcmp(key, "packed")) ctx->opt_packed = (int)value;
+  else if (!strcmp(key, "fuse2")) ctx->opt_fuse2 = (int)value;
+  else if (!strcmp(key, "fuse2_warps")) ctx->opt_f2_warps = (int)value;
+  else if (!strcmp(key, "fuse2_rows")) ctx->opt_f2_rows = (int)value;
   else return fail("unknown option '%s'", key);
   if (sync_all(ctx)) return 1;
   resolve_options(ctx);
@@ -1031,13 +1103,16 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
   info->cells_per_thread = ctx->V;
   info->threads_per_block = ctx->tpb;
   info->streaming = ctx->streaming;
-  info->steps_per_launch = ctx->persistent ? ctx->chunk_steps : 1;
+  info->steps_per_launch = ctx->persistent ? ctx->chunk_steps : (ctx->fuse2 ? 2 : 1);
   info->steps_done = ctx->steps_done;
   info->kernel_launches = ctx->launches;
   info->partials_per_step = ctx->per_step;
   if (ctx->persistent)
     snprintf(info->kernel_name, sizeof info->kernel_name, "persistent_kernel<V=%d,tpb=%d,packed=%d>", ctx->V, ctx->tpb,
              ctx->packed);
+  else if (ctx->fuse2)
+    snprintf(info->kernel_name, sizeof info->kernel_name, "fuse2_kernel<W=%d,packed=%d,rows=%d>", ctx->f2_warps,
+             ctx->packed, ctx->f2_rows);
   else
     snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d,tps=%d,packed=%d>", ctx->V,
              ctx->streaming, ctx->tpb, ctx->tps, ctx->packed);

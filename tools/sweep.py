@@ -33,6 +33,19 @@ def main():
     sim.upload(cells, obstacles)
     print(f"upload {time.time()-t0:.2f}s", flush=True)
     for var in args.variants.split(","):
+        if var.startswith("f2"):          # f2:<warps>:<packed>:<seg_rows>
+            _, w, pk, sr = var.split(":")
+            for k, v in (("persistent", 0), ("cells_per_thread", 4), ("fuse2", 1), ("fuse2_warps", int(w)),
+                         ("packed", int(pk)), ("fuse2_rows", int(sr))):
+                sim.set_option(k, v)
+            sim.run(args.warmup + (args.warmup & 1))
+            sim.sync()
+            ms = sim.run_timed(args.steps)
+            mlups = args.nx * args.ny * args.steps / (ms * 1e-3) / 1e6
+            print(f"{sim.info()['kernel_name']}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
+                  f"{mlups*72/1e3:,.0f} GB/s algorithmic  {mlups*72/1e3/peak*100:.1f}% of measured HBM copy", flush=True)
+            sim.set_option("fuse2", 0)
+            continue
         parts = [int(x) for x in var.split(":")]
         V, tpb, st = parts[:3]
         sim.set_option("persistent", parts[3] if len(parts) > 3 else 0)
