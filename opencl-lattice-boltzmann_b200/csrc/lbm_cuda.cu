@@ -138,7 +138,7 @@ struct lbm_ctx {
   long long launches = 0;
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0;
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_prefetch = 1, opt_f2_tma = 1;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256;
   int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
@@ -237,7 +237,8 @@ int alloc_slab(lbm_ctx* ctx, Slab& s) {
   s.layout.flags_offset = 2 * s.layout.buf_floats * (long long)sizeof(float);
   s.layout.mask_offset = s.layout.flags_offset + 256;
   const size_t mask_bytes = sizeof(uint32_t) * (size_t)ctx->mask_pitch * (size_t)(s.rows + 2);
-  const size_t arena_bytes = (size_t)s.layout.mask_offset + mask_bytes;
+  // + tail pad: the two-step kernel's bulk copies read whole TX+8-float rows and may run past a short row
+  const size_t arena_bytes = (size_t)s.layout.mask_offset + mask_bytes + 8192;
   // stream-ordered clears: a plain cudaMemset runs on the legacy stream, which the slab's
   // non-blocking stream does not wait for, and could still be clearing when lbm_upload copies
   CK(cudaMalloc(&s.arena, arena_bytes));
@@ -468,24 +469,51 @@ int launch_persistent(const Variant& v, const lbm::PersistArgs& pa, long long gr
 #undef CALL_
 }
 
-template <int W, bool PACKED, int MINB>
+template <int W, bool PACKED, int MINB, bool PREFETCH>
 int launch_fuse2_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
   static bool configured[64] = {};
   int dev = 0;
   CK(cudaGetDevice(&dev));
   if (dev < 64 && !configured[dev]) {
-    CK(cudaFuncSetAttribute(lbm::fuse2_kernel<W, PACKED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(lbm::fuse2_kernel<W, PACKED, MINB, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             lbm::fuse2_smem_bytes<W>()));
     configured[dev] = true;
   }
-  lbm::fuse2_kernel<W, PACKED, MINB><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2_smem_bytes<W>(), st>>>(fa);
+  lbm::fuse2_kernel<W, PACKED, MINB, PREFETCH><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2_smem_bytes<W>(), st>>>(fa);
   return 0;
 }
 
-int launch_fuse2(int warps, int packed, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
-  if (warps == 2) return packed ? launch_fuse2_t<2, true, 5>(fa, grid, st) : launch_fuse2_t<2, false, 5>(fa, grid, st);
-  if (warps == 8) return packed ? launch_fuse2_t<8, true, 1>(fa, grid, st) : launch_fuse2_t<8, false, 1>(fa, grid, st);
-  return packed ? launch_fuse2_t<4, true, 3>(fa, grid, st) : launch_fuse2_t<4, false, 3>(fa, grid, st);
+template <bool PACKED, bool PREFETCH>
+int launch_fuse2_w(int warps, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  // resident blocks per SM the registers are bounded for: with prefetch one fewer (more live registers)
+  if (warps == 2) return launch_fuse2_t<2, PACKED, PREFETCH ? 4 : 5, PREFETCH>(fa, grid, st);
+  if (warps == 8) return launch_fuse2_t<8, PACKED, 1, PREFETCH>(fa, grid, st);
+  return launch_fuse2_t<4, PACKED, PREFETCH ? 2 : 3, PREFETCH>(fa, grid, st);
+}
+
+template <int W, bool PACKED, int MINB>
+int launch_fuse2_tma_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  static bool configured[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    CK(cudaFuncSetAttribute(lbm::fuse2_tma_kernel<W, PACKED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            lbm::fuse2_tma_smem_bytes<W>()));
+    configured[dev] = true;
+  }
+  lbm::fuse2_tma_kernel<W, PACKED, MINB><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2_tma_smem_bytes<W>(), st>>>(fa);
+  return 0;
+}
+
+int launch_fuse2_tma(int warps, int packed, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  if (warps == 2) return packed ? launch_fuse2_tma_t<2, true, 5>(fa, grid, st) : launch_fuse2_tma_t<2, false, 5>(fa, grid, st);
+  if (warps == 8) return packed ? launch_fuse2_tma_t<8, true, 1>(fa, grid, st) : launch_fuse2_tma_t<8, false, 1>(fa, grid, st);
+  return packed ? launch_fuse2_tma_t<4, true, 3>(fa, grid, st) : launch_fuse2_tma_t<4, false, 3>(fa, grid, st);
+}
+
+int launch_fuse2(int warps, int packed, int prefetch, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  if (packed) return prefetch ? launch_fuse2_w<true, true>(warps, fa, grid, st) : launch_fuse2_w<true, false>(warps, fa, grid, st);
+  return prefetch ? launch_fuse2_w<false, true>(warps, fa, grid, st) : launch_fuse2_w<false, false>(warps, fa, grid, st);
 }
 
 // local row of global row ny-2 in this slab, or -1
@@ -662,7 +690,10 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         fa.partials1 = s.partials + (long long)in_chunk * s.pstride;
         fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
         fa.per_step = s.pstride;
-        if (launch_fuse2(ctx->f2_warps, ctx->packed, fa, (long long)s.f2_strips * s.f2_segs_y, s.stream)) return 1;
+        const long long f2grid = (long long)s.f2_strips * s.f2_segs_y;
+        if (ctx->opt_f2_tma ? launch_fuse2_tma(ctx->f2_warps, ctx->packed, fa, f2grid, s.stream)
+                            : launch_fuse2(ctx->f2_warps, ctx->packed, ctx->opt_f2_prefetch, fa, f2grid, s.stream))
+          return 1;
       } else {
         if (s.pstride > s.blocks)   // (tiny grids only) the step kernel writes s.blocks partials: clear the rest
           CK(cudaMemsetAsync(a.partials + s.blocks, 0, sizeof(double2) * (size_t)(s.pstride - s.blocks), s.stream));
@@ -1055,6 +1086,8 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "fuse2")) ctx->opt_fuse2 = (int)value;
   else if (!strcmp(key, "fuse2_warps")) ctx->opt_f2_warps = (int)value;
   else if (!strcmp(key, "fuse2_rows")) ctx->opt_f2_rows = (int)value;
+  else if (!strcmp(key, "fuse2_prefetch")) ctx->opt_f2_prefetch = value ? 1 : 0;
+  else if (!strcmp(key, "fuse2_tma")) ctx->opt_f2_tma = value ? 1 : 0;
   else return fail("unknown option '%s'", key);
   if (sync_all(ctx)) return 1;
   resolve_options(ctx);
@@ -1111,8 +1144,8 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
     snprintf(info->kernel_name, sizeof info->kernel_name, "persistent_kernel<V=%d,tpb=%d,packed=%d>", ctx->V, ctx->tpb,
              ctx->packed);
   else if (ctx->fuse2)
-    snprintf(info->kernel_name, sizeof info->kernel_name, "fuse2_kernel<W=%d,packed=%d,rows=%d>", ctx->f2_warps,
-             ctx->packed, ctx->f2_rows);
+    snprintf(info->kernel_name, sizeof info->kernel_name, "%s<W=%d,packed=%d,rows=%d>",
+             ctx->opt_f2_tma ? "fuse2_tma_kernel" : "fuse2_kernel", ctx->f2_warps, ctx->packed, ctx->f2_rows);
   else
     snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d,tps=%d,packed=%d>", ctx->V,
              ctx->streaming, ctx->tpb, ctx->tps, ctx->packed);

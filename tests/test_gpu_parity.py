@@ -96,13 +96,15 @@ FUSE2_SHAPES = [(256, 64), (1024, 16), (100, 37), (4096, 8), (520, 40), (8, 4), 
 
 @pytest.mark.parametrize("nx,ny", FUSE2_SHAPES)
 @pytest.mark.parametrize("nsteps", [8, 7])
-def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps):
+@pytest.mark.parametrize("tma", [1, 0])
+def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps, tma):
     """Temporal blocking (two time steps per HBM pass, step-1 rows in a shared-memory ring) gives the
     same bits as the oracle; 7 steps = three fused pairs + one single step."""
     p, cells, obstacles = random_case(nx, ny, seed=nx + ny, walls=False)
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, nsteps, reference_order=(nx % 128 == 0))
-    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, nsteps, options={"persistent": 0, "fuse2": 1})
-    assert info["kernel_name"].startswith("fuse2_kernel") and info["steps_per_launch"] == 2
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, nsteps,
+                                      options={"persistent": 0, "fuse2": 1, "fuse2_tma": tma})
+    assert info["kernel_name"].startswith("fuse2_tma_kernel" if tma else "fuse2_kernel") and info["steps_per_launch"] == 2
     assert np.array_equal(bits(got_cells), bits(ref_cells))
     np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
 
@@ -110,12 +112,14 @@ def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps):
 @pytest.mark.parametrize("warps", [2, 4, 8])
 @pytest.mark.parametrize("packed", [0, 1])
 @pytest.mark.parametrize("seg_rows", [4, 10, 256])
-def test_two_step_kernel_variants(lbm, oracle, warps, packed, seg_rows):
+@pytest.mark.parametrize("tma", [1, 0])
+def test_two_step_kernel_variants(lbm, oracle, warps, packed, seg_rows, tma):
     """Strip width, row-segment length (redundant warm-up rows at every segment start) and packed
     arithmetic do not change a bit; av_vels equal the one-step kernel's bitwise."""
     p, cells, obstacles = random_case(1280, 37, seed=77, walls=False)
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 6)
-    opts = {"persistent": 0, "fuse2": 1, "fuse2_warps": warps, "fuse2_rows": seg_rows, "packed": packed}
+    opts = {"persistent": 0, "fuse2": 1, "fuse2_warps": warps, "fuse2_rows": seg_rows, "packed": packed,
+            "fuse2_tma": tma}
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 6, options=opts)
     assert f"W={warps}" in info["kernel_name"]
     assert np.array_equal(bits(got_cells), bits(ref_cells))
@@ -131,7 +135,7 @@ def test_two_step_kernel_row_slabs(lbm, nslabs):
     a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 9, options={"persistent": 0, "fuse2": 0, "cells_per_thread": 4})
     b_cells, b_av, info = run_gpu(lbm, p, cells, obstacles, 9, devices=[0] * nslabs,
                                   options={"fuse2": 1, "fuse2_rows": 8})
-    assert info["nslabs"] == nslabs and info["kernel_name"].startswith("fuse2_kernel")
+    assert info["nslabs"] == nslabs and info["kernel_name"].startswith("fuse2_")
     assert np.array_equal(bits(a_cells), bits(b_cells))
     assert np.array_equal(bits(a_av), bits(b_av))
 
