@@ -138,7 +138,7 @@ struct lbm_ctx {
   long long launches = 0;
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_prefetch = 1, opt_f2_tma = 1;
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_prefetch = 1, opt_f2_tma = 1, opt_f2_l2ahead = 0;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256;
   int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
@@ -687,6 +687,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         fa.strips = s.f2_strips;
         fa.segs_y = s.f2_segs_y;
         fa.seg_rows = ctx->f2_rows;
+        fa.l2_ahead = ctx->opt_f2_l2ahead;
         fa.partials1 = s.partials + (long long)in_chunk * s.pstride;
         fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
         fa.per_step = s.pstride;
@@ -1088,6 +1089,7 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "fuse2_rows")) ctx->opt_f2_rows = (int)value;
   else if (!strcmp(key, "fuse2_prefetch")) ctx->opt_f2_prefetch = value ? 1 : 0;
   else if (!strcmp(key, "fuse2_tma")) ctx->opt_f2_tma = value ? 1 : 0;
+  else if (!strcmp(key, "fuse2_l2_ahead")) ctx->opt_f2_l2ahead = (int)std::max(0L, std::min(64L, value));
   else return fail("unknown option '%s'", key);
   if (sync_all(ctx)) return 1;
   resolve_options(ctx);

@@ -32,6 +32,7 @@ struct Fuse2Args {
   int strips;              // column strips of TX cells
   int segs_y;              // row segments per strip
   int seg_rows;            // rows per segment
+  int l2_ahead;            // TMA kernel: rows ahead of the stage load that are prefetched into L2 (0 = off; measured: off is best)
   double2* partials1;      // Σ|u| partials of the first step  [per_step entries, first strips*segs_y used]
   double2* partials2;      // Σ|u| partials of the second step
   long long per_step;      // entries per step in the partial buffer (the tail is zeroed here)
@@ -350,6 +351,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uin
                : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 template <int W>
 constexpr int fuse2_tma_smem_bytes() { return (27 + NSPEEDS) * (128 * W + 8) * (int)sizeof(float) + 16; }
 
@@ -412,6 +417,16 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
     for (int k = 0; k < NSPEEDS; k++) {
       const int dy = (k == 2 || k == 5 || k == 6) ? -1 : (k == 4 || k == 7 || k == 8) ? 1 : 0;
       tma_load_1d(stage + k * RS, base + k * ps + (long long)dy * a.pitch, RS * (uint32_t)sizeof(float), full);
+    }
+    // optional: pull the rows a few iterations ahead from HBM into L2 (measured slower at 16384^2: 128 -> 110-120 GLUPS)
+    const int rp = r + fa.l2_ahead;
+    if (fa.l2_ahead > 0 && rp <= ye) {
+      const float* pb = a.src + (long long)rp * a.pitch + (x0 - 4);
+#pragma unroll
+      for (int k = 0; k < NSPEEDS; k++) {
+        const int dy = (k == 2 || k == 5 || k == 6) ? -1 : (k == 4 || k == 7 || k == 8) ? 1 : 0;
+        tma_prefetch_l2(pb + k * ps + (long long)dy * a.pitch, RS * (uint32_t)sizeof(float));
+      }
     }
   };
 

@@ -37,6 +37,7 @@ def main():
             _, w, pk, sr, *rest = var.split(":")
             pf = int(rest[0]) if rest else 1
             sim.set_option("fuse2_tma", int(rest[1]) if len(rest) > 1 else 1)
+            sim.set_option("fuse2_l2_ahead", int(rest[2]) if len(rest) > 2 else 0)
             for k, v in (("persistent", 0), ("cells_per_thread", 4), ("fuse2", 1), ("fuse2_warps", int(w)),
                          ("packed", int(pk)), ("fuse2_rows", int(sr)), ("fuse2_prefetch", pf)):
                 sim.set_option(k, v)
@@ -44,7 +45,7 @@ def main():
             sim.sync()
             ms = sim.run_timed(args.steps)
             mlups = args.nx * args.ny * args.steps / (ms * 1e-3) / 1e6
-            print(f"{sim.info()['kernel_name']} prefetch={pf}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
+            print(f"{sim.info()['kernel_name']} prefetch={pf} l2_ahead={int(rest[2]) if len(rest) > 2 else 0}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
                   f"{mlups*72/1e3:,.0f} GB/s algorithmic  {mlups*72/1e3/peak*100:.1f}% of measured HBM copy", flush=True)
             sim.set_option("fuse2", 0)
             continue
