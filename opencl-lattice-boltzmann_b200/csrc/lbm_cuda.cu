@@ -196,7 +196,7 @@ void resolve_options(lbm_ctx* ctx) {
   // cache-hint mode of the lattice accesses (lbm_kernels.cuh); plain ld.global.nc / st.global measured best
   ctx->streaming = (ctx->opt_streaming == 1) ? 1 : 0;
   ctx->tps = (ctx->opt_tps == 768) ? 768 : 1024;
-  ctx->packed = (ctx->V > 1) && (ctx->opt_packed >= 0 ? ctx->opt_packed != 0 : 0);
+  ctx->packed = (ctx->V > 1) && (ctx->opt_packed >= 0 ? ctx->opt_packed != 0 : 0);   // refined below for fuse2
   long long per_step = 0;
   const int wpb = tpb / 32;
   for (auto& s : ctx->slabs) {
@@ -211,11 +211,15 @@ void resolve_options(lbm_ctx* ctx) {
   // two time steps per HBM pass (lbm_fuse2.cuh): 128-bit kernel only, lattices streamed from HBM,
   // every slab of the ring at least 4 rows (an even split, so every rank decides alike)
   ctx->f2_warps = (ctx->opt_f2_warps == 2 || ctx->opt_f2_warps == 4 || ctx->opt_f2_warps == 8) ? ctx->opt_f2_warps : 4;
-  ctx->f2_rows = ctx->opt_f2_rows >= 4 ? ctx->opt_f2_rows : 256;
+  ctx->f2_rows = ctx->opt_f2_rows >= 4 ? ctx->opt_f2_rows : 128;
   const long long total_slabs = (long long)ctx->nranks * (long long)ctx->slabs.size();
   const bool can_fuse = !ctx->persistent && V == 4 && nx >= 8 && (ctx->p.ny / total_slabs) >= 4;
-  ctx->fuse2 = can_fuse && (ctx->opt_fuse2 >= 0 ? ctx->opt_fuse2 != 0 : 0);
+  // auto: on whenever the lattice is streamed from HBM (measured 128.5 vs 95 GLUPS at 16384^2)
+  ctx->fuse2 = can_fuse && (ctx->opt_fuse2 >= 0 ? ctx->opt_fuse2 != 0 : 1);
   if (ctx->fuse2) {
+    // the two-step kernel is issue-bound, not HBM-bound: the packed fp32x2 arithmetic pays there
+    if (ctx->opt_packed < 0) ctx->packed = 1;
+    if (ctx->packed && ctx->opt_tps != 1024) ctx->tps = 768;   // odd tail step: packed needs ~80 registers
     ctx->chunk_steps = std::max(2, ctx->chunk_steps);
     const int tx = 128 * ctx->f2_warps;
     for (auto& s : ctx->slabs) {

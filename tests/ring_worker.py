@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--ny", type=int, default=203)
     ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--split", default="11,14")  # two run() calls
+    ap.add_argument("--fuse2", type=int, default=-1)
     args = ap.parse_args()
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -34,7 +35,8 @@ def main():
 
     p, cells, obstacles = helpers.random_case(args.nx, args.ny, seed=4242, walls=False)
     y0, rows = lbm.cabi.partition_rows(args.ny, world, rank)
-    sim = lbm.cabi.Simulation(p, slab=(local, rank, world, y0, rows), options={"cells_per_thread": 4})
+    sim = lbm.cabi.Simulation(p, slab=(local, rank, world, y0, rows),
+                              options={"cells_per_thread": 4, "fuse2": args.fuse2, "fuse2_rows": 8})
     blobs = [None] * world
     dist.all_gather_object(blobs, sim.export_blob())
     sim.connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
@@ -71,7 +73,7 @@ def main():
             av1 = one.download_av_vels(args.steps)
         av_same = np.array_equal(helpers.bits(av), helpers.bits(av1))
         ok = same and av_ok and av_same
-        print(f"RING world={world} lattice_bit_exact={same} av_close={av_ok} av_bitwise_vs_1gpu={av_same}", flush=True)
+        print(f"RING world={world} kernel={sim.info()['kernel_name']} lattice_bit_exact={same} av_close={av_ok} av_bitwise_vs_1gpu={av_same}", flush=True)
     sim.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -41,7 +41,7 @@ def test_kernel_variants_bit_exact(lbm, oracle, V, tpb, streaming):
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 5)
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 5,
                                       options={"cells_per_thread": V, "threads_per_block": tpb, "streaming": streaming,
-                                               "persistent": 0})
+                                               "persistent": 0, "fuse2": 0})
     assert info["cells_per_thread"] == V and info["threads_per_block"] == tpb and info["streaming"] == streaming
     assert info["kernel_name"].startswith("step_kernel")
     assert np.array_equal(bits(got_cells), bits(ref_cells))
@@ -85,7 +85,7 @@ def test_packed_and_register_bound_variants_bit_exact(lbm, oracle, tps, packed, 
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 5)
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 5,
                                       options={"persistent": persistent, "threads_per_sm": tps, "packed": packed,
-                                               "cells_per_thread": V})
+                                               "cells_per_thread": V, "fuse2": 0})
     assert f"packed={packed}" in info["kernel_name"]
     assert np.array_equal(bits(got_cells), bits(ref_cells))
     np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)

@@ -16,12 +16,14 @@ def _gpu_count():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_ring_matches_oracle(world):
+@pytest.mark.parametrize("fuse2", [1, 0])
+def test_ring_matches_oracle(world, fuse2):
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29510 + world),
-           os.path.join(ROOT, "tests", "ring_worker.py")]
+           os.path.join(ROOT, "tests", "ring_worker.py"), "--fuse2", str(fuse2)]
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "lattice_bit_exact=True" in proc.stdout and "av_bitwise_vs_1gpu=True" in proc.stdout
+    assert ("fuse2_tma_kernel" in proc.stdout) == bool(fuse2)
