@@ -90,18 +90,32 @@ def main():
     rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
     per_launch = sum(a + b for a, b in zip(rd, wr)) / len(rd)
     kname = data[0][hdr.index("Kernel Name")]
-    # "void step_kernel<4, 1, 256>(StepArgs)" -> bench.py's info name
+    # ncu's demangled name -> the name lbm_get_info reports (bench.py's config.kernel)
     import re
+    steps = 1
     m = re.search(r"step_kernel<(\d+), (\d+), (\d+), (\d+), (\d+)>", kname)
-    name = (f"step_kernel<V={m.group(1)},hint={m.group(2)},tpb={m.group(3)},tps={m.group(4)},packed={m.group(5)}>"
-            if m else kname)
-    rec = {"kernel": name, "ncu_kernel_name": kname, "cells_per_launch": cells,
+    name = kname
+    if m:
+        name = f"step_kernel<V={m.group(1)},hint={m.group(2)},tpb={m.group(3)},tps={m.group(4)},packed={m.group(5)}>"
+    m = re.search(r"(fuse2_tma_kernel|fuse2_kernel)<(\d+), (\d+)", kname)
+    if m:
+        steps = 2
+        rows = sys.argv[4] if len(sys.argv) > 4 else "128"
+        name = f"{m.group(1)}<W={m.group(2)},packed={m.group(3)},rows={rows}>"
+    rec = {"kernel": name, "ncu_kernel_name": kname, "cells_per_launch": cells, "steps_per_launch": steps,
            "dram_bytes_read_per_launch": sum(rd) / len(rd), "dram_bytes_write_per_launch": sum(wr) / len(wr),
-           "dram_bytes_per_launch": per_launch, "algorithmic_bytes_per_launch": 72 * cells,
-           "traffic_over_algorithmic": per_launch / (72 * cells), "launches_captured": len(rd),
+           "dram_bytes_per_launch": per_launch, "algorithmic_bytes_per_launch": 72 * cells * steps,
+           "traffic_over_algorithmic": per_launch / (72 * cells * steps), "launches_captured": len(rd),
            "source": f"ncu --set full --clock-control none, {os.path.basename(rep)} ({tag})"}
-    with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json"), "w") as fp:
-        json.dump(rec, fp, indent=1)
+    path = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    try:
+        with open(path) as fp:
+            table = json.load(fp)
+    except Exception:
+        table = {}
+    table[name] = rec
+    with open(path, "w") as fp:
+        json.dump(table, fp, indent=1)
     print(json.dumps(rec, indent=1))
 
 
