@@ -355,10 +355,6 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <int W>
 constexpr int fuse2_tma_smem_bytes() { return (27 + NSPEEDS) * (128 * W + 8) * (int)sizeof(float) + 16; }
 
@@ -372,8 +368,7 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
   float* ring_n = stage + NSPEEDS * RS;              // [2][3][RS] planes 4,7,8 of step t+1
   float* ring_m = ring_n + 2 * 3 * RS;               // [3][3][RS] planes 0,1,3
   float* ring_s = ring_m + 3 * 3 * RS;               // [4][3][RS] planes 2,5,6
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring_s + 4 * 3 * RS);   // stage filled (TMA bytes landed)
-  uint64_t* empty = full + 1;                                          // stage read into registers by every thread
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_s + 4 * 3 * RS);
   __shared__ double part_hi[2][W], part_lo[2][W];
 
   const StepArgs& a = fa.s;
@@ -402,10 +397,7 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
   const bool wrap_r = need_r && xb + V >= nx;   // x+4 wraps to 0
   const bool touches_bottom = (ys == 0), touches_top = (ye == rows);
 
-  if (threadIdx.x == 0) {
-    mbar_init(full, 1);
-    mbar_init(empty, 32 * (W + 1));
-  }
+  if (threadIdx.x == 0) mbar_init(full, 1);
   if (a.edge_count != nullptr && (touches_bottom || touches_top)) {
     if (threadIdx.x == 0) {
       if (touches_top) wait_epoch(a.flag_from_up, a.epoch - 1);
@@ -448,8 +440,6 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
   const int xh = (lane == 0) ? ((x0 == 0) ? nx - 1 : x0 - 1) : ((x0 + ncol >= nx) ? 0 : x0 + ncol);
   const int xhw = (xh == 0) ? nx - 1 : xh - 1;
   const int xhe = (xh + 1 >= nx) ? 0 : xh + 1;
-  // a halo column inside the row has its nine inputs in the stage; one across the x wrap does not
-  const bool halo_wrap = (lane == 0) ? (x0 == 0) : (x0 + ncol >= nx);
   auto load_scalars = [&](int r) {
     const float* s_mid = a.src + (long long)r * a.pitch;
     const float* s_south = s_mid - a.pitch;
@@ -465,17 +455,15 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
       we7 = load_one<0>(s_north + 7 * ps);
     }
     if (halo_warp && lane < 2) {
-      if (halo_wrap) {
-        ht[0] = load_one<0>(s_mid + 0 * ps + xh);
-        ht[1] = load_one<0>(s_mid + 1 * ps + xhw);
-        ht[2] = load_one<0>(s_south + 2 * ps + xh);
-        ht[3] = load_one<0>(s_mid + 3 * ps + xhe);
-        ht[4] = load_one<0>(s_north + 4 * ps + xh);
-        ht[5] = load_one<0>(s_south + 5 * ps + xhw);
-        ht[6] = load_one<0>(s_south + 6 * ps + xhe);
-        ht[7] = load_one<0>(s_north + 7 * ps + xhe);
-        ht[8] = load_one<0>(s_north + 8 * ps + xhw);
-      }
+      ht[0] = load_one<0>(s_mid + 0 * ps + xh);
+      ht[1] = load_one<0>(s_mid + 1 * ps + xhw);
+      ht[2] = load_one<0>(s_south + 2 * ps + xh);
+      ht[3] = load_one<0>(s_mid + 3 * ps + xhe);
+      ht[4] = load_one<0>(s_north + 4 * ps + xh);
+      ht[5] = load_one<0>(s_south + 5 * ps + xhw);
+      ht[6] = load_one<0>(s_south + 6 * ps + xhe);
+      ht[7] = load_one<0>(s_north + 7 * ps + xhe);
+      ht[8] = load_one<0>(s_north + 8 * ps + xhw);
       hfluid = ((__ldg(a.mask + (long long)r * a.mask_pitch + (xh >> 5)) >> (xh & 31)) & 1u) == 0u;
     }
   };
@@ -490,11 +478,8 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
     v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
   };
 
-  // ---- phase 1: step t -> t+1 of row r, inputs from the stage.  Every thread arrives on `empty` as
-  // soon as its stage reads are in registers; the halo warp's lane 0 then refills the stage with row
-  // r+1 (issue_next), a whole iteration before phase 1 of row r+1 needs it. ----
-  uint32_t parity_e = 0;
-  auto phase1 = [&](int r, bool issue_next) {
+  // ---- phase 1: step t -> t+1 of row r, inputs from the stage ----
+  auto phase1 = [&](int r) {
     const bool accel = (global_row(r, fa.y0, fa.ny) == accel_g);
     if (!halo_warp) {
       float q[NSPEEDS][V];
@@ -511,7 +496,6 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
       }
       if (need_l) { f1 = stage[1 * RS + c - 1]; f5 = stage[5 * RS + c - 1]; f8 = stage[8 * RS + c - 1]; }
       if (need_r) { f3 = stage[3 * RS + c + V]; f6 = stage[6 * RS + c + V]; f7 = stage[7 * RS + c + V]; }
-      mbar_arrive(empty);
       if (wrap_l) { f1 = we1; f5 = we5; f8 = we8; }
       if (wrap_r) { f3 = we3; f6 = we6; f7 = we7; }
       float l1 = __shfl_up_sync(FULL, q[1][V - 1], 1);
@@ -541,25 +525,11 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
         for (int s = 16; s >= 1; s >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(FULL, tot, s));
         if (lane == 0) dd_add(hi1, lo1, (double)tot, 0.0);
       }
-    } else {
-      const int idx = (lane == 0) ? 3 : 4 + ncol;      // the halo column's index in stage / ring rows
-      if (lane < 2 && !halo_wrap) {
-        ht[0] = stage[0 * RS + idx];     ht[1] = stage[1 * RS + idx - 1]; ht[2] = stage[2 * RS + idx];
-        ht[3] = stage[3 * RS + idx + 1]; ht[4] = stage[4 * RS + idx];     ht[5] = stage[5 * RS + idx - 1];
-        ht[6] = stage[6 * RS + idx + 1]; ht[7] = stage[7 * RS + idx + 1]; ht[8] = stage[8 * RS + idx - 1];
-      }
-      mbar_arrive(empty);
-      if (lane == 0) {
-        if (issue_next) {
-          mbar_wait(empty, parity_e);    // every thread has read the stage
-          issue_row(r + 1);
-        }
-      }
-      parity_e ^= 1;
-      if (lane >= 2) return;
+    } else if (lane < 2) {
       float o[NSPEEDS];
       collide_cell(ht, hfluid, a.omega, o);
       if (accel) accelerate_cell(o, hfluid, a.w1, a.w2);
+      const int idx = (lane == 0) ? 3 : 4 + ncol;
       float* n = rn(r) + idx;
       float* m = rm(r) + idx;
       float* so = rs(r) + idx;
