@@ -211,11 +211,22 @@ void resolve_options(lbm_ctx* ctx) {
   // two time steps per HBM pass (lbm_fuse2.cuh): 128-bit kernel only, lattices streamed from HBM,
   // every slab of the ring at least 4 rows (an even split, so every rank decides alike)
   ctx->f2_warps = (ctx->opt_f2_warps == 2 || ctx->opt_f2_warps == 4 || ctx->opt_f2_warps == 8) ? ctx->opt_f2_warps : 4;
-  ctx->f2_rows = ctx->opt_f2_rows >= 4 ? ctx->opt_f2_rows : 128;
   const long long total_slabs = (long long)ctx->nranks * (long long)ctx->slabs.size();
   const bool can_fuse = !ctx->persistent && V == 4 && nx >= 8 && (ctx->p.ny / total_slabs) >= 4;
-  // auto: on whenever the lattice is streamed from HBM (measured 128.5 vs 95 GLUPS at 16384^2)
-  ctx->fuse2 = can_fuse && (ctx->opt_fuse2 >= 0 ? ctx->opt_fuse2 != 0 : 1);
+  // rows per segment: every segment start recomputes two warm-up rows, so long segments are cheaper, but
+  // the grid (strips x segments) should fill the ~444 resident blocks of a B200 a few times over
+  {
+    const long long strips = (nx + 128 * ctx->f2_warps - 1) / (128 * ctx->f2_warps);
+    // the smallest slab of the even split: the same number on every rank of a ring, so all decide alike
+    const long long min_rows = std::max(1LL, ctx->p.ny / total_slabs);
+    // measured best (tools/f2_rows_test.py): 64 rows, 32 when that leaves fewer than ~1000 blocks
+    const int seg = (min_rows * strips / 1000 >= 64) ? 64 : 32;
+    ctx->f2_rows = ctx->opt_f2_rows >= 4 ? ctx->opt_f2_rows : seg;
+    const long long blocks = strips * ((min_rows + ctx->f2_rows - 1) / ctx->f2_rows);
+    // auto: on when the lattice is streamed from HBM and the grid fills the GPU at least once
+    // (measured 128.4 vs 95 GLUPS at 16384^2); smaller lattices keep the one-step kernel
+    ctx->fuse2 = can_fuse && (ctx->opt_fuse2 >= 0 ? ctx->opt_fuse2 != 0 : blocks >= 444);
+  }
   if (ctx->fuse2) {
     // the two-step kernel is issue-bound, not HBM-bound: the packed fp32x2 arithmetic pays there
     if (ctx->opt_packed < 0) ctx->packed = 1;
