@@ -412,7 +412,8 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000,
+                    help="timed LBM time steps (the reference decks run 20 000 - 80 000 per upload)")
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU,

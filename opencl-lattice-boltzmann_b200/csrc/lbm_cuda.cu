@@ -92,7 +92,8 @@ struct Slab {
   double* av_lo = nullptr;
   long long av_capacity = 0;
   Neighbour up, down;
-  unsigned long long edge_expected = 0;  // edge-row completions counted so far on this slab (edge_target of the next launch)
+  unsigned long long edge_expected = 0;      // bottom-edge completions counted so far on this slab (edge_target of the next launch)
+  unsigned long long edge_expected_top = 0;  // same for the top edge
   int f2_strips = 1, f2_segs_y = 1;      // tiling of the two-step kernel
   long long pstride = 0;                 // partial entries per step = max(step-kernel blocks, two-step blocks)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -687,10 +688,24 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         a.edge_count = f + 2;
         a.peer_up_flag = nb_flags(s.up) + 1;
         a.peer_down_flag = nb_flags(s.down) + 0;
-        // completions this launch adds to each edge counter: warps of the two edge rows, or edge blocks
-        s.edge_expected += pair ? (unsigned long long)s.f2_strips
-                                : (unsigned long long)ctx->segs * (unsigned long long)std::min(GHOST, s.rows);
+        // completions this launch adds to each edge counter: the warps of the two edge rows (one-step
+        // kernel), or the blocks of the segments holding rows 0,1 / rows-2,rows-1 (two-step kernel)
+        if (pair) {
+          int top_segs = 0, bottom_segs = 0;
+          for (int sy = 0; sy < s.f2_segs_y; sy++) {
+            const int ys = sy * ctx->f2_rows, ye = std::min(s.rows, ys + ctx->f2_rows);
+            if (ys < 2) bottom_segs++;
+            if (ye >= s.rows - 1) top_segs++;
+          }
+          s.edge_expected += (unsigned long long)s.f2_strips * bottom_segs;
+          s.edge_expected_top += (unsigned long long)s.f2_strips * top_segs;
+        } else {
+          const unsigned long long n = (unsigned long long)ctx->segs * (unsigned long long)std::min(GHOST, s.rows);
+          s.edge_expected += n;
+          s.edge_expected_top += n;
+        }
         a.edge_target = s.edge_expected;
+        a.edge_target_top = s.edge_expected_top;
       }
       a.epoch = ctx->epoch;
       if (pair) {

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_kernel(const __grid_
   const int ncol = min(TX, nx - x0);            // columns of this strip (a multiple of 4)
   const int j0 = (warp * 32 + lane) * V;        // the thread's first column within the strip (body warps)
   const bool active = !halo_warp && j0 < ncol;
-  const bool touches_bottom = (ys == 0), touches_top = (ye == rows);
+  // segments that read ghost rows or whose rows 0,1 / rows-2,rows-1 are stored into a neighbour's ghost rows
+  const bool touches_bottom = (ys < 2), touches_top = (ye >= rows - 1);
 
   if (a.edge_count != nullptr && (touches_bottom || touches_top)) {  // ring: neighbours' previous epoch complete
     if (threadIdx.x == 0) {
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_kernel(const __grid_
       __threadfence_system();
       st_release_sys(a.peer_down_flag, a.epoch);
     }
-    if (touches_top && atomicAdd(a.edge_count + 1, 1ULL) + 1ULL == a.edge_target) {
+    if (touches_top && atomicAdd(a.edge_count + 1, 1ULL) + 1ULL == a.edge_target_top) {
       __threadfence_system();
       st_release_sys(a.peer_up_flag, a.epoch);
     }
@@ -395,7 +396,8 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
   const bool need_r = active && (lane == 31 || j0 + V >= ncol);
   const bool wrap_l = need_l && xb == 0;        // x-1 wraps to nx-1: not in the stage
   const bool wrap_r = need_r && xb + V >= nx;   // x+4 wraps to 0
-  const bool touches_bottom = (ys == 0), touches_top = (ye == rows);
+  // segments that read ghost rows or whose rows 0,1 / rows-2,rows-1 are stored into a neighbour's ghost rows
+  const bool touches_bottom = (ys < 2), touches_top = (ye >= rows - 1);
 
   if (threadIdx.x == 0) mbar_init(full, 1);
   if (a.edge_count != nullptr && (touches_bottom || touches_top)) {
@@ -638,7 +640,7 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
       __threadfence_system();
       st_release_sys(a.peer_down_flag, a.epoch);
     }
-    if (touches_top && atomicAdd(a.edge_count + 1, 1ULL) + 1ULL == a.edge_target) {
+    if (touches_top && atomicAdd(a.edge_count + 1, 1ULL) + 1ULL == a.edge_target_top) {
       __threadfence_system();
       st_release_sys(a.peer_up_flag, a.epoch);
     }

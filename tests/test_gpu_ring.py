@@ -15,14 +15,16 @@ def _gpu_count():
     return lbm.cabi.load_library().lbm_device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world,ny", [(2, 203), (2, 50), (4, 203), (8, 203)])
 @pytest.mark.parametrize("fuse2", [1, 0])
-def test_ring_matches_oracle(world, fuse2):
+def test_ring_matches_oracle(world, ny, fuse2):
+    """ny = 50 on two ranks and 203 on eight give slabs of 25 rows: with 8-row segments the last segment
+    holds one row, so the second edge row (rows-2) lives in another block of the two-step kernel."""
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29510 + world),
-           os.path.join(ROOT, "tests", "ring_worker.py"), "--fuse2", str(fuse2)]
+           os.path.join(ROOT, "tests", "ring_worker.py"), "--fuse2", str(fuse2), "--ny", str(ny)]
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "lattice_bit_exact=True" in proc.stdout and "av_bitwise_vs_1gpu=True" in proc.stdout
