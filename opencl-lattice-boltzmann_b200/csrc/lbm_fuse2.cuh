@@ -484,20 +484,15 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
   auto phase1 = [&](int r) {
     const bool accel = (global_row(r, fa.y0, fa.ny) == accel_g);
     if (!halo_warp) {
+      // shared-memory reads are unconditional: every index used lies inside the row buffers, and what
+      // inactive lanes (columns beyond the strip) compute from it is never stored or summed
       float q[NSPEEDS][V];
 #pragma unroll
-      for (int k = 0; k < NSPEEDS; k++)
-#pragma unroll
-        for (int j = 0; j < V; j++) q[k][j] = 0.0f;
-      float f1 = 0.f, f5 = 0.f, f8 = 0.f, f3 = 0.f, f6 = 0.f, f7 = 0.f;
+      for (int k = 0; k < NSPEEDS; k++) lds4(stage + k * RS + c, q[k]);
       uint32_t bits = 0;
-      if (active) {
-#pragma unroll
-        for (int k = 0; k < NSPEEDS; k++) lds4(stage + k * RS + c, q[k]);
-        bits = __ldg(a.mask + (long long)r * a.mask_pitch + (xb >> 5)) >> (xb & 31);
-      }
-      if (need_l) { f1 = stage[1 * RS + c - 1]; f5 = stage[5 * RS + c - 1]; f8 = stage[8 * RS + c - 1]; }
-      if (need_r) { f3 = stage[3 * RS + c + V]; f6 = stage[6 * RS + c + V]; f7 = stage[7 * RS + c + V]; }
+      if (active) bits = __ldg(a.mask + (long long)r * a.mask_pitch + (xb >> 5)) >> (xb & 31);
+      float f1 = stage[1 * RS + c - 1], f5 = stage[5 * RS + c - 1], f8 = stage[8 * RS + c - 1];
+      float f3 = stage[3 * RS + c + V], f6 = stage[6 * RS + c + V], f7 = stage[7 * RS + c + V];
       if (wrap_l) { f1 = we1; f5 = we5; f8 = we8; }
       if (wrap_r) { f3 = we3; f6 = we6; f7 = we7; }
       float l1 = __shfl_up_sync(FULL, q[1][V - 1], 1);
@@ -525,7 +520,7 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
       if (r >= ys && r < ye) {
 #pragma unroll
         for (int s = 16; s >= 1; s >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(FULL, tot, s));
-        if (lane == 0) dd_add(hi1, lo1, (double)tot, 0.0);
+        dd_add(hi1, lo1, (double)tot, 0.0);   // every lane keeps the same sum: no branch
       }
     } else if (lane < 2) {
       float o[NSPEEDS];
@@ -548,20 +543,13 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
     const float* so = rs(y - 1) + c;   // planes 2,5,6 of row y-1
     const float* n = rn(y + 1) + c;    // planes 4,7,8 of row y+1
     float q[NSPEEDS][V];
-#pragma unroll
-    for (int k = 0; k < NSPEEDS; k++)
-#pragma unroll
-      for (int j = 0; j < V; j++) q[k][j] = 0.0f;
-    float f1 = 0.f, f5 = 0.f, f8 = 0.f, f3 = 0.f, f6 = 0.f, f7 = 0.f;
+    lds4(m + 0 * RS, q[0]); lds4(m + 1 * RS, q[1]); lds4(m + 2 * RS, q[3]);
+    lds4(so + 0 * RS, q[2]); lds4(so + 1 * RS, q[5]); lds4(so + 2 * RS, q[6]);
+    lds4(n + 0 * RS, q[4]); lds4(n + 1 * RS, q[7]); lds4(n + 2 * RS, q[8]);
     uint32_t bits = 0;
-    if (active) {
-      lds4(m + 0 * RS, q[0]); lds4(m + 1 * RS, q[1]); lds4(m + 2 * RS, q[3]);
-      lds4(so + 0 * RS, q[2]); lds4(so + 1 * RS, q[5]); lds4(so + 2 * RS, q[6]);
-      lds4(n + 0 * RS, q[4]); lds4(n + 1 * RS, q[7]); lds4(n + 2 * RS, q[8]);
-      bits = __ldg(a.mask + (long long)y * a.mask_pitch + (xb >> 5)) >> (xb & 31);
-    }
-    if (need_l) { f1 = m[1 * RS - 1]; f5 = so[1 * RS - 1]; f8 = n[2 * RS - 1]; }
-    if (need_r) { f3 = m[2 * RS + V]; f6 = so[2 * RS + V]; f7 = n[1 * RS + V]; }
+    if (active) bits = __ldg(a.mask + (long long)y * a.mask_pitch + (xb >> 5)) >> (xb & 31);
+    const float f1 = m[1 * RS - 1], f5 = so[1 * RS - 1], f8 = n[2 * RS - 1];
+    const float f3 = m[2 * RS + V], f6 = so[2 * RS + V], f7 = n[1 * RS + V];
     float l1 = __shfl_up_sync(FULL, q[1][V - 1], 1);
     float l5 = __shfl_up_sync(FULL, q[5][V - 1], 1);
     float l8 = __shfl_up_sync(FULL, q[8][V - 1], 1);
@@ -593,7 +581,7 @@ __global__ void __launch_bounds__(32 * (W + 1), MINB) fuse2_tma_kernel(const __g
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) tot = __fadd_rn(tot, __shfl_xor_sync(FULL, tot, s));
-    if (lane == 0) dd_add(hi2, lo2, (double)tot, 0.0);
+    dd_add(hi2, lo2, (double)tot, 0.0);
   };
 
   // prologue: rows ys-1 and ys of step t+1, then row ys+1's inputs in flight
