@@ -78,6 +78,7 @@ struct Slab {
   float* arena = nullptr;
   ArenaLayout layout{};
   uint32_t* mask = nullptr;      // row 0 of the obstacle bit mask (inside the arena; ghost rows -1 and rows)
+  int* stage = nullptr;          // upload staging buffer for the obstacle ints
   double2* partials = nullptr;   // chunk_steps x blocks_per_step block partials
   double2* scratch = nullptr;    // chunk_steps x splits range sums of av_finalize_kernel
   unsigned int* tickets = nullptr;
@@ -916,6 +917,7 @@ void lbm_destroy(lbm_ctx* ctx) {
     if (s.up.ipc && s.up.arena) cudaIpcCloseMemHandle(s.up.arena);
     if (s.down.ipc && s.down.arena) cudaIpcCloseMemHandle(s.down.arena);
     if (s.arena) cudaFree(s.arena);
+    if (s.stage) cudaFree(s.stage);
     if (s.partials) { cudaFree(s.partials); cudaFree(s.scratch); cudaFree(s.tickets); }
     if (s.progress) cudaFree(s.progress);
     if (s.av_hi) cudaFree(s.av_hi);
@@ -949,25 +951,28 @@ int lbm_upload(lbm_ctx* ctx, const float* cells_soa, const int* obstacles) {
   for (auto& s : ctx->slabs) {
     if (set_device(s)) return 1;
     const size_t row_off = (size_t)(s.y0 - ctx->y0) * nx;
-    for (int k = 0; k < 9; k++)
-      CK(cudaMemcpy2DAsync(s.row0(0) + k * s.layout.plane_stride, sizeof(float) * ctx->pitch,
-                           cells_soa + k * host_plane + row_off, sizeof(float) * nx, sizeof(float) * nx, s.rows,
-                           cudaMemcpyHostToDevice, s.stream));
-    // obstacle ints -> bit mask, staged through a bounded device buffer
+    for (int k = 0; k < 9; k++) {
+      float* dst = s.row0(0) + k * s.layout.plane_stride;
+      const float* src = cells_soa + k * host_plane + row_off;
+      if (ctx->pitch == nx)   // rows are contiguous on both sides: one flat copy per plane (full PCIe rate)
+        CK(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)nx * s.rows, cudaMemcpyHostToDevice, s.stream));
+      else
+        CK(cudaMemcpy2DAsync(dst, sizeof(float) * ctx->pitch, src, sizeof(float) * nx, sizeof(float) * nx, s.rows,
+                             cudaMemcpyHostToDevice, s.stream));
+    }
+    // obstacle ints -> bit mask, staged through a bounded device buffer kept for later uploads; copies and
+    // pack kernels are stream-ordered, so the buffer can be reused without host synchronisation
     const int stage_rows = (int)std::max<long long>(1, std::min<long long>(s.rows, (64LL << 20) / std::max(1, nx)));
-    int* stage = nullptr;
-    CK(cudaMalloc(&stage, sizeof(int) * (size_t)stage_rows * nx));
+    if (!s.stage) CK(cudaMalloc(&s.stage, sizeof(int) * (size_t)stage_rows * nx));
     for (int r0 = 0; r0 < s.rows; r0 += stage_rows) {
       const int nr = std::min(stage_rows, s.rows - r0);
-      CK(cudaMemcpyAsync(stage, obstacles + row_off + (size_t)r0 * nx, sizeof(int) * (size_t)nr * nx,
+      CK(cudaMemcpyAsync(s.stage, obstacles + row_off + (size_t)r0 * nx, sizeof(int) * (size_t)nr * nx,
                          cudaMemcpyHostToDevice, s.stream));
       dim3 grid(ctx->mask_pitch, nr);
-      lbm::pack_obstacles_kernel<<<grid, 32, 0, s.stream>>>(stage, nx, s.mask + (size_t)r0 * ctx->mask_pitch,
+      lbm::pack_obstacles_kernel<<<grid, 32, 0, s.stream>>>(s.stage, nx, s.mask + (size_t)r0 * ctx->mask_pitch,
                                                             ctx->mask_pitch);
       ctx->launches++;
-      CK(cudaStreamSynchronize(s.stream));  // `stage` and pageable host memory are reused
     }
-    CK(cudaFree(stage));
     if (s.av_hi) CK(cudaMemsetAsync(s.av_hi, 0, sizeof(double) * s.av_capacity, s.stream));
     if (s.av_lo) CK(cudaMemsetAsync(s.av_lo, 0, sizeof(double) * s.av_capacity, s.stream));
   }
@@ -994,10 +999,15 @@ int lbm_download_cells(lbm_ctx* ctx, float* cells_soa) {
   for (auto& s : ctx->slabs) {
     if (set_device(s)) return 1;
     const size_t row_off = (size_t)(s.y0 - ctx->y0) * nx;
-    for (int k = 0; k < 9; k++)
-      CK(cudaMemcpy2DAsync(cells_soa + k * host_plane + row_off, sizeof(float) * nx,
-                           s.row0(ctx->cur) + k * s.layout.plane_stride, sizeof(float) * ctx->pitch,
-                           sizeof(float) * nx, s.rows, cudaMemcpyDeviceToHost, s.stream));
+    for (int k = 0; k < 9; k++) {
+      float* dst = cells_soa + k * host_plane + row_off;
+      const float* src = s.row0(ctx->cur) + k * s.layout.plane_stride;
+      if (ctx->pitch == nx)
+        CK(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)nx * s.rows, cudaMemcpyDeviceToHost, s.stream));
+      else
+        CK(cudaMemcpy2DAsync(dst, sizeof(float) * nx, src, sizeof(float) * ctx->pitch, sizeof(float) * nx, s.rows,
+                             cudaMemcpyDeviceToHost, s.stream));
+    }
   }
   return sync_all(ctx);
 }
