@@ -221,8 +221,9 @@ void resolve_options(lbm_ctx* ctx) {
     const long long strips = (nx + 128 * ctx->f2_warps - 1) / (128 * ctx->f2_warps);
     // the smallest slab of the even split: the same number on every rank of a ring, so all decide alike
     const long long min_rows = std::max(1LL, ctx->p.ny / total_slabs);
-    // measured best (tools/f2_rows_test.py): 64 rows, 32 when that leaves fewer than ~1000 blocks
-    const int seg = (min_rows * strips / 1000 >= 64) ? 64 : 32;
+    // measured best (tools/f2_rows_test.py): about 2048 blocks, between 16 and 64 rows per segment
+    int seg = 64;
+    while (seg > 16 && min_rows * strips / seg < 2048) seg >>= 1;
     ctx->f2_rows = ctx->opt_f2_rows >= 4 ? ctx->opt_f2_rows : seg;
     const long long blocks = strips * ((min_rows + ctx->f2_rows - 1) / ctx->f2_rows);
     // auto: on when the lattice is streamed from HBM and the grid fills the GPU at least once
