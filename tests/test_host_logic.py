@@ -57,6 +57,16 @@ def test_obstacle_errors_python(tmp_path, text, message):
         decks.load_deck(pf, of)
 
 
+def test_empty_obstacle_file_and_duplicates(tmp_path):
+    """An empty obstacle list is legal (the reference's fscanf loop simply ends, d2q9-bgk.c:571); duplicate
+    lines are not counted twice (d2q9-bgk.c:583-585)."""
+    pf = write(tmp_path, "p.params", GOOD_PARAMS)
+    p, cells, obstacles = decks.load_deck(pf, write(tmp_path, "empty.dat", ""))
+    assert obstacles.sum() == 0 and np.float32(p.free_cells_inv) == np.float32(1.0) / np.float32(48)
+    p, cells, obstacles = decks.load_deck(pf, write(tmp_path, "dup.dat", "1 1 1\n1 1 1\n2 3 1\n"))
+    assert obstacles.sum() == 2 and np.float32(p.free_cells_inv) == np.float32(1.0) / np.float32(46)
+
+
 def test_param_errors_python(tmp_path):
     with pytest.raises(decks.DeckError, match="could not open input parameter file"):
         decks.read_params(str(tmp_path / "missing.params"))
