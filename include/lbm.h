@@ -155,12 +155,19 @@ int lbm_run_timed(lbm_ctx *ctx, int nsteps, float *ms);
 
 /* Tuning knobs, before lbm_upload: "cells_per_thread" (0 = auto, 1, 2, 4),
  * "threads_per_block", "threads_per_sm" (register bound: 512, 768, 1024), "streaming" (0: default
- * caching, 1: .cs hints), "persistent" (-1 auto, 0, 1), "global_barrier", "chunk_steps".  Unknown key -> non-zero. */
+ * caching, 1: .cs hints), "persistent" (-1 auto, 0, 1), "global_barrier", "chunk_steps", "fuse2" (-1 auto, 0, 1: two time steps per
+ * launch), "fuse2_tma" (which two-step kernel: 0 register prefetch, 1 TMA staging, 2 re-pipelined TMA
+ * staging = default), "fuse2_rows", "fuse2_mode" (bit 0: one reciprocal/sqrt range check per thread; bit 1: dry run without
+ * arithmetic for bandwidth experiments — garbage results).  Unknown key -> non-zero. */
 int lbm_set_option(lbm_ctx *ctx, const char *key, long value);
 int lbm_get_info(lbm_ctx *ctx, lbm_info *info);
 /* Debug canary: number of non-zero floats in the pad columns [nx, pitch) of every row of both
  * lattice buffers (cleared at creation, never written by a correct kernel). */
 int lbm_debug_pad_nonzero(lbm_ctx *ctx, long long *count);
+/* Debug check of the two-step kernel's branch-light reciprocal / square root (lbm_kernels.cuh
+ * rcp_rn_fast, sqrt_rn_fast) against the correctly rounded __frcp_rn / __fsqrt_rn over all 2^32
+ * float bit patterns on the current device; both counts must come back 0. */
+int lbm_debug_fastmath_mismatches(unsigned long long *rcp_bad, unsigned long long *sqrt_bad);
 int lbm_device_count(void);
 int lbm_abi_version(void);
 

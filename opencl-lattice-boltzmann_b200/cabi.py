@@ -20,7 +20,7 @@ EXPORTS = [
     "lbm_create", "lbm_create_on", "lbm_create_slab", "lbm_partition_rows", "lbm_export_size", "lbm_export",
     "lbm_connect", "lbm_destroy", "lbm_upload", "lbm_halo_push", "lbm_download_cells", "lbm_download_av_vels",
     "lbm_download_av_sums", "lbm_download_final_state", "lbm_combine_av_sums", "lbm_host_alloc", "lbm_host_free", "lbm_run", "lbm_sync",
-    "lbm_run_timed", "lbm_set_option", "lbm_get_info", "lbm_debug_pad_nonzero", "lbm_device_count", "lbm_abi_version", "lbm_last_error",
+    "lbm_run_timed", "lbm_set_option", "lbm_get_info", "lbm_debug_pad_nonzero", "lbm_debug_fastmath_mismatches", "lbm_device_count", "lbm_abi_version", "lbm_last_error",
 ]
 
 
@@ -86,12 +86,23 @@ def load_library(path: str | None = None):
     lib.lbm_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     lib.lbm_get_info.argtypes = [vp, C.POINTER(LbmInfo)]
     lib.lbm_debug_pad_nonzero.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.lbm_debug_fastmath_mismatches.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.lbm_device_count.argtypes = []
     lib.lbm_abi_version.argtypes = []
     lib.lbm_last_error.argtypes = []
     lib.lbm_last_error.restype = C.c_char_p
     _lib = lib
     return lib
+
+
+def fastmath_mismatches():
+    """lbm_debug_fastmath_mismatches: (rcp, sqrt) mismatch counts of the two-step kernel's fast
+    reciprocal / square root against the correctly rounded built-ins over all 2^32 floats."""
+    lib = load_library()
+    a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+    if lib.lbm_debug_fastmath_mismatches(C.byref(a), C.byref(b)) != 0:
+        raise LbmError(lib.lbm_last_error().decode())
+    return int(a.value), int(b.value)
 
 
 def partition_rows(ny: int, nparts: int, part: int):

@@ -9,6 +9,7 @@
 #include "lbm.h"
 #include "lbm_kernels.cuh"
 #include "lbm_fuse2.cuh"
+#include "lbm_fuse2p.cuh"
 
 #include <cuda_runtime.h>
 
@@ -140,9 +141,10 @@ struct lbm_ctx {
   long long launches = 0;
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_prefetch = 1, opt_f2_tma = 1, opt_f2_l2ahead = 0;
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_prefetch = 1, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256;
+  int f2_kernel = 2;           // 0: fuse2_kernel (register prefetch), 1: fuse2_tma_kernel, 2: fuse2p_kernel (W = 4 only)
   int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
   long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
   float w1 = 0.f, w2 = 0.f;
@@ -213,6 +215,7 @@ void resolve_options(lbm_ctx* ctx) {
   // two time steps per HBM pass (lbm_fuse2.cuh): 128-bit kernel only, lattices streamed from HBM,
   // every slab of the ring at least 4 rows (an even split, so every rank decides alike)
   ctx->f2_warps = (ctx->opt_f2_warps == 2 || ctx->opt_f2_warps == 4 || ctx->opt_f2_warps == 8) ? ctx->opt_f2_warps : 4;
+  ctx->f2_kernel = (ctx->opt_f2_tma == 2 && ctx->f2_warps != 4) ? 1 : ctx->opt_f2_tma;   // fuse2p_kernel: 512-column strips only
   const long long total_slabs = (long long)ctx->nranks * (long long)ctx->slabs.size();
   const bool can_fuse = !ctx->persistent && V == 4 && nx >= 8 && (ctx->p.ny / total_slabs) >= 4;
   // rows per segment: every segment start recomputes two warm-up rows, so long segments are cheaper, but
@@ -529,6 +532,36 @@ int launch_fuse2_tma(int warps, int packed, const lbm::Fuse2Args& fa, long long 
   return packed ? launch_fuse2_tma_t<4, true, 3>(fa, grid, st) : launch_fuse2_tma_t<4, false, 3>(fa, grid, st);
 }
 
+template <int W, bool PACKED, bool FULLW, int MODE>
+int launch_fuse2p_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  static bool configured[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    CK(cudaFuncSetAttribute(lbm::fuse2p_kernel<W, PACKED, FULLW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            lbm::fuse2p_smem_bytes<W>()));
+    CK(cudaFuncSetAttribute(lbm::fuse2p_kernel<W, PACKED, FULLW, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    configured[dev] = true;
+  }
+  lbm::fuse2p_kernel<W, PACKED, FULLW, MODE><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2p_smem_bytes<W>(), st>>>(fa);
+  return 0;
+}
+
+// the re-pipelined two-step kernel (lbm_fuse2p.cuh): 512-column strips.  mode bit 0: one reciprocal /
+// square-root range check per thread instead of per pair; bit 1: dry run (bandwidth experiments only)
+int launch_fuse2p(int packed, bool fullw, int mode, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+#define F2P_(P, F)                                                                  \
+  do {                                                                              \
+    if (mode & 2) return launch_fuse2p_t<4, P, F, 2>(fa, grid, st);                 \
+    if (P && (mode & 1)) return launch_fuse2p_t<4, P, F, 1>(fa, grid, st);          \
+    return launch_fuse2p_t<4, P, F, 0>(fa, grid, st);                               \
+  } while (0)
+  if (packed) { if (fullw) F2P_(true, true); else F2P_(true, false); }
+  if (fullw) F2P_(false, true); else F2P_(false, false);
+#undef F2P_
+}
+
 int launch_fuse2(int warps, int packed, int prefetch, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
   if (packed) return prefetch ? launch_fuse2_w<true, true>(warps, fa, grid, st) : launch_fuse2_w<true, false>(warps, fa, grid, st);
   return prefetch ? launch_fuse2_w<false, true>(warps, fa, grid, st) : launch_fuse2_w<false, false>(warps, fa, grid, st);
@@ -724,9 +757,12 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
         fa.per_step = s.pstride;
         const long long f2grid = (long long)s.f2_strips * s.f2_segs_y;
-        if (ctx->opt_f2_tma ? launch_fuse2_tma(ctx->f2_warps, ctx->packed, fa, f2grid, s.stream)
-                            : launch_fuse2(ctx->f2_warps, ctx->packed, ctx->opt_f2_prefetch, fa, f2grid, s.stream))
-          return 1;
+        const int rc = ctx->f2_kernel == 2
+                           ? launch_fuse2p(ctx->packed, ctx->p.nx % 512 == 0, ctx->opt_f2_mode, fa, f2grid, s.stream)
+                       : ctx->f2_kernel == 1
+                           ? launch_fuse2_tma(ctx->f2_warps, ctx->packed, fa, f2grid, s.stream)
+                           : launch_fuse2(ctx->f2_warps, ctx->packed, ctx->opt_f2_prefetch, fa, f2grid, s.stream);
+        if (rc) return 1;
       } else {
         if (s.pstride > s.blocks)   // (tiny grids only) the step kernel writes s.blocks partials: clear the rest
           CK(cudaMemsetAsync(a.partials + s.blocks, 0, sizeof(double2) * (size_t)(s.pstride - s.blocks), s.stream));
@@ -1129,7 +1165,8 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "fuse2_warps")) ctx->opt_f2_warps = (int)value;
   else if (!strcmp(key, "fuse2_rows")) ctx->opt_f2_rows = (int)value;
   else if (!strcmp(key, "fuse2_prefetch")) ctx->opt_f2_prefetch = value ? 1 : 0;
-  else if (!strcmp(key, "fuse2_tma")) ctx->opt_f2_tma = value ? 1 : 0;
+  else if (!strcmp(key, "fuse2_tma")) ctx->opt_f2_tma = (int)std::max(0L, std::min(2L, value));
+  else if (!strcmp(key, "fuse2_mode")) ctx->opt_f2_mode = (int)(value & 3);
   else if (!strcmp(key, "fuse2_l2_ahead")) ctx->opt_f2_l2ahead = (int)std::max(0L, std::min(64L, value));
   else return fail("unknown option '%s'", key);
   if (sync_all(ctx)) return 1;
@@ -1166,6 +1203,23 @@ int lbm_debug_pad_nonzero(lbm_ctx* ctx, long long* count) {
   return 0;
 }
 
+int lbm_debug_fastmath_mismatches(unsigned long long* rcp_bad, unsigned long long* sqrt_bad) {
+  // rcp_rn_fast / sqrt_rn_fast + their range tests (lbm_kernels.cuh) against __frcp_rn / __fsqrt_rn
+  // over ALL 2^32 float bit patterns, on the current device.
+  if (!rcp_bad || !sqrt_bad) return fail("lbm_debug_fastmath_mismatches: NULL argument");
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+  CK(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  lbm::fastmath_check_kernel<<<148 * 8, 256>>>(d);
+  CK(cudaGetLastError());
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d));
+  *rcp_bad = h[0];
+  *sqrt_bad = h[1];
+  return 0;
+}
+
 int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
   if (!ctx || !info) return fail("lbm_get_info: NULL argument");
   memset(info, 0, sizeof *info);
@@ -1188,7 +1242,8 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
              ctx->packed);
   else if (ctx->fuse2)
     snprintf(info->kernel_name, sizeof info->kernel_name, "%s<W=%d,packed=%d,rows=%d>",
-             ctx->opt_f2_tma ? "fuse2_tma_kernel" : "fuse2_kernel", ctx->f2_warps, ctx->packed, ctx->f2_rows);
+             ctx->f2_kernel == 2 ? "fuse2p_kernel" : ctx->f2_kernel == 1 ? "fuse2_tma_kernel" : "fuse2_kernel", ctx->f2_warps,
+             ctx->packed, ctx->f2_rows);
   else
     snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d,tps=%d,packed=%d>", ctx->V,
              ctx->streaming, ctx->tpb, ctx->tps, ctx->packed);

@@ -1,0 +1,417 @@
+// lbm_fuse2p.cuh — the two-step march of lbm_fuse2.cuh (fuse2_tma_kernel) re-pipelined.
+//
+// Same tiling, same shared-memory ring, same arithmetic and the same results (lattice and
+// Σ|u| partials bit-identical to fuse2_tma_kernel, hence to the one-step kernel and the
+// oracle).  What changed is everything that kept the warps waiting (ncu of the
+// predecessor: 48 % issue slots, 10 % of warp time in the mbarrier wait, 7 % on the
+// obstacle-word load, 6 % at the barrier, a 157-instruction TMA issue on warp 0):
+//
+//   * the step-t rows of the NEXT iteration are requested as soon as the stage buffer
+//     has been read into registers, not after phase 1: every body warp arrives on an
+//     `empty` mbarrier once its loads are done, and the halo warp — which has time to
+//     spare — waits on it and issues the bulk copies, so no body warp waits or issues and
+//     the copies are in flight for a whole row time (phase 1's arithmetic + phase 2)
+//     instead of phase 2 only.  (First cut: the last warp out of the stage issued; that
+//     warp then reached the row barrier ~150 instructions late, 15 % barrier stall.);
+//   * the nine per-plane source pointers sit in a shared-memory table: issuing a row is
+//     one 64-bit add per copy;
+//   * the strip's obstacle words travel with the stage copies (a tenth bulk copy of 64 bytes
+//     into a four-row ring): phase 1 and, an iteration later, phase 2 read them from shared
+//     memory — no global load, no register carried across iterations;
+//   * the halo warp takes its two columns from the stage (interior strips); its remaining
+//     global loads (periodic wrap, obstacle bit) are issued after the barrier, where it
+//     idles anyway;
+//   * reciprocal / square root: one range check per thread instead of one guarded
+//     region per value, Newton steps in packed FFMA2 (compute_quad, lbm_kernels.cuh);
+//   * the Σ|u| butterflies are deferred by half an iteration so their shuffle latency
+//     overlaps the other phase's arithmetic;
+//   * FULLW (nx a multiple of the strip width): no per-lane activity predicates.
+//
+// Replaces two iterations of the reference's host loop d2q9-bgk.c:221-238
+// (2 x accelerate_flow + 2 x timestep, kernels.cl:9-231).
+#pragma once
+
+#include "lbm_fuse2.cuh"
+
+namespace lbm {
+
+template <int W>
+constexpr int fuse2p_smem_bytes() {
+  return (27 + NSPEEDS) * (128 * W + 8) * (int)sizeof(float) + 24 + NSPEEDS * 8 + 4 * 4 * W * (int)sizeof(uint32_t) + 6 * 4 * (int)sizeof(float);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// MODE bit 0: one reciprocal / square-root range check per thread instead of per pair (compute_quad<JOINT>).
+// MODE bit 1: dry run for bandwidth experiments — same memory traffic, no arithmetic (results are garbage).
+template <int W, bool PACKED, bool FULLW, int MODE>
+__global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_constant__ Fuse2Args fa) {
+  constexpr int V = 4;
+  constexpr int TX = 128 * W;
+  constexpr int RS = TX + 8;        // row stride per plane: columns x0-4 .. x0+TX+3 (cell j at index 4+j)
+  constexpr bool JOINT = (MODE & 1) != 0, DRY = (MODE & 2) != 0;
+  extern __shared__ __align__(128) float smem[];
+  float* stage = smem;                               // [9][RS]   step-t rows for the next phase 1
+  float* ring_n = stage + NSPEEDS * RS;              // [2][3][RS] planes 4,7,8 of step t+1
+  float* ring_m = ring_n + 2 * 3 * RS;               // [3][3][RS] planes 0,1,3
+  float* ring_s = ring_m + 3 * 3 * RS;               // [4][3][RS] planes 2,5,6
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_s + 4 * 3 * RS);
+  uint64_t* empty = full + 1;
+  const float** ptab = reinterpret_cast<const float**>(full + 3);   // per plane: source of column x0-4 of local row 0
+  uint32_t* mring = reinterpret_cast<uint32_t*>(ptab + NSPEEDS);    // [4][4*W] obstacle words of the strip, rows r & 3
+  constexpr int MW = 4 * W;         // obstacle words per strip row
+  float* wst = reinterpret_cast<float*>(mring + 4 * MW);            // [6][4] periodic x wrap of the outermost strips:
+                                                                    // planes 1,5,8 at columns nx-4..nx-1, planes 3,6,7 at 0..3
+  constexpr bool MTMA = FULLW;      // mask rows travel with the stage copies (needs 16-byte aligned strip starts)
+  __shared__ double part_hi[2][W], part_lo[2][W];
+
+  const StepArgs& a = fa.s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool halo_warp = (warp == W);
+  const int nx = a.nx, rows = a.rows;
+  const long long ps = a.plane_stride;
+
+  int strip, sy;
+  {
+    const int b = blockIdx.x, ns = fa.strips;
+    if (fa.segs_y < 2 || b < ns) { sy = b / ns; strip = b - sy * ns; }
+    else if (b < 2 * ns) { sy = fa.segs_y - 1; strip = b - ns; }
+    else { sy = 1 + (b - 2 * ns) / ns; strip = (b - 2 * ns) % ns; }
+  }
+  const int ys = sy * fa.seg_rows, ye = min(rows, ys + fa.seg_rows);
+  const int x0 = strip * TX;
+  const int ncol = FULLW ? TX : min(TX, nx - x0);
+  const int j0 = (warp * 32 + lane) * V;
+  const int c = 4 + j0;                         // the thread's first column in stage / ring rows
+  const int xb = x0 + j0;
+  const bool active = !halo_warp && (FULLW || j0 < ncol);
+  const bool touches_bottom = (ys < 2), touches_top = (ye >= rows - 1);
+  if (!halo_warp && lane < 2) {   // the warp's Σ|u| accumulators of the two steps
+    part_hi[lane][warp] = 0.0;
+    part_lo[lane][warp] = 0.0;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(empty, W);
+  }
+  if (threadIdx.x < NSPEEDS) {   // which source row plane k is pulled from (kernels.cl:104-112)
+    const int k = threadIdx.x;
+    const int dy = (k == 2 || k == 5 || k == 6) ? -1 : (k == 4 || k == 7 || k == 8) ? 1 : 0;
+    ptab[k] = a.src + k * ps + (long long)dy * a.pitch + (x0 - 4);
+  }
+  if (a.edge_count != nullptr && (touches_bottom || touches_top)) {
+    if (threadIdx.x == 0) {
+      if (touches_top) wait_epoch(a.flag_from_up, a.epoch - 1);
+      if (touches_bottom) wait_epoch(a.flag_from_down, a.epoch - 1);
+    }
+  }
+  __syncthreads();
+
+  const int accel_g = fa.ny - 2;
+
+  const bool strip_first = (x0 == 0), strip_last = (x0 + ncol >= nx);
+  auto issue_row = [&](int r) {   // one thread: the nine plane-rows phase 1 of row r needs -> stage
+    mbar_expect_tx(full, NSPEEDS * RS * (uint32_t)sizeof(float) + (MTMA ? MW * (uint32_t)sizeof(uint32_t) : 0u) +
+                             (strip_first ? 48u : 0u) + (strip_last ? 48u : 0u));
+    const long long off = (long long)r * a.pitch;
+    if (strip_first) {   // x-1 of column 0 is column nx-1 (kernels.cl:102): planes 1,5,8, columns nx-4..nx-1
+      tma_load_1d(wst + 0, ptab[1] + off + nx, 16u, full);
+      tma_load_1d(wst + 4, ptab[5] + off + nx, 16u, full);
+      tma_load_1d(wst + 8, ptab[8] + off + nx, 16u, full);
+    }
+    if (strip_last) {    // x+1 of column nx-1 is column 0 (kernels.cl:100-101): planes 3,6,7, columns 0..3
+      tma_load_1d(wst + 12, ptab[3] + off + (4 - x0), 16u, full);
+      tma_load_1d(wst + 16, ptab[6] + off + (4 - x0), 16u, full);
+      tma_load_1d(wst + 20, ptab[7] + off + (4 - x0), 16u, full);
+    }
+#pragma unroll
+    for (int k = 0; k < NSPEEDS; k++) tma_load_1d(stage + k * RS, ptab[k] + off, RS * (uint32_t)sizeof(float), full);
+    if constexpr (MTMA)   // the strip's obstacle words of row r: read by phase 1 of row r and, an iteration later, by phase 2
+      tma_load_1d(mring + (r & 3) * MW, a.mask + (long long)r * a.mask_pitch + (x0 >> 5), MW * (uint32_t)sizeof(uint32_t), full);
+  };
+  // body warps, once they hold their share of the stage in registers: the halo warp (which has the
+  // time) waits for all of them and requests the next row — nobody on the critical path waits or issues
+  auto stage_consumed = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty);
+  };
+  // the block barrier, reached from two different loops (body warps / halo warp)
+  auto block_sync = [&]() { asm volatile("bar.sync 0;" ::: "memory"); };
+
+  // ring addressing: row r's planes 4,7,8 / 0,1,3 / 2,5,6 (index within the group: 0,1,2)
+  auto rn = [&](int r) { return ring_n + ((r + 4) & 1) * (3 * RS); };
+  auto rm = [&](int r) { return ring_m + ((r + 6) % 3) * (3 * RS); };
+  auto rs = [&](int r) { return ring_s + (r & 3) * (3 * RS); };
+
+  uint32_t parity = 0;
+  if (threadIdx.x == 0) issue_row(ys - 1);
+
+  if (halo_warp) {
+    // =====================================================================================
+    // halo warp: lanes 0 / 1 advance the column left / right of the strip by one step
+    // (phase 1 only), from the stage, or from global memory where the column is the
+    // periodic wrap (kernels.cl:100-102).  Same waits, counts and barriers as the body warps.
+    // =====================================================================================
+    const bool hl = lane < 2;
+    const int xh = (lane == 0) ? ((x0 == 0) ? nx - 1 : x0 - 1) : ((x0 + ncol >= nx) ? 0 : x0 + ncol);
+    const int xhw = (xh == 0) ? nx - 1 : xh - 1;
+    const int xhe = (xh + 1 >= nx) ? 0 : xh + 1;
+    const bool h_global = hl && ((lane == 0) ? (x0 == 0) : (x0 + ncol >= nx));   // wrapped column: not in the stage
+    const int hidx = (lane == 0) ? 3 : 4 + ncol;                               // its index in stage / ring rows
+    float ht[NSPEEDS];
+    uint32_t hmask = 0, eparity = 0;
+#pragma unroll
+    for (int k = 0; k < NSPEEDS; k++) ht[k] = 0.0f;
+    auto halo_prefetch = [&](int r) {   // global loads, one row ahead: obstacle bit (+ the wrapped column)
+      if (hl) hmask = __ldg(a.mask + (long long)r * a.mask_pitch + (xh >> 5));
+      if (h_global) {
+        const float* s_mid = a.src + (long long)r * a.pitch;
+        const float* s_south = s_mid - a.pitch;
+        const float* s_north = s_mid + a.pitch;
+        ht[0] = load_one<0>(s_mid + 0 * ps + xh);
+        ht[1] = load_one<0>(s_mid + 1 * ps + xhw);
+        ht[2] = load_one<0>(s_south + 2 * ps + xh);
+        ht[3] = load_one<0>(s_mid + 3 * ps + xhe);
+        ht[4] = load_one<0>(s_north + 4 * ps + xh);
+        ht[5] = load_one<0>(s_south + 5 * ps + xhw);
+        ht[6] = load_one<0>(s_south + 6 * ps + xhe);
+        ht[7] = load_one<0>(s_north + 7 * ps + xhe);
+        ht[8] = load_one<0>(s_north + 8 * ps + xhw);
+      }
+    };
+    auto halo_row = [&](int r, int next_r, bool more) {
+      mbar_wait(full, parity);
+      parity ^= 1;
+      if (hl && !h_global) {
+        ht[0] = stage[0 * RS + hidx];
+        ht[1] = stage[1 * RS + hidx - 1];
+        ht[2] = stage[2 * RS + hidx];
+        ht[3] = stage[3 * RS + hidx + 1];
+        ht[4] = stage[4 * RS + hidx];
+        ht[5] = stage[5 * RS + hidx - 1];
+        ht[6] = stage[6 * RS + hidx + 1];
+        ht[7] = stage[7 * RS + hidx + 1];
+        ht[8] = stage[8 * RS + hidx - 1];
+      }
+      if (hl) {
+        const bool accel = (global_row(r, fa.y0, fa.ny) == accel_g);
+        const bool hfluid = ((hmask >> (xh & 31)) & 1u) == 0u;
+        float o[NSPEEDS];
+        collide_cell(ht, hfluid, a.omega, o);
+        if (accel) accelerate_cell(o, hfluid, a.w1, a.w2);
+        float* n = rn(r) + hidx;
+        float* m = rm(r) + hidx;
+        float* so = rs(r) + hidx;
+        m[0 * RS] = o[0]; m[1 * RS] = o[1]; m[2 * RS] = o[3];
+        so[0 * RS] = o[2]; so[1 * RS] = o[5]; so[2 * RS] = o[6];
+        n[0 * RS] = o[4]; n[1 * RS] = o[7]; n[2 * RS] = o[8];
+      }
+      if (more) {   // the halo's own stage values have been consumed above; now wait for the body warps' reads
+        mbar_wait(empty, eparity);
+        if (lane == 0) issue_row(next_r);
+      }
+      eparity ^= 1;
+    };
+    halo_prefetch(ys - 1);
+    for (int r = ys - 1; r <= ys; r++) {
+      halo_row(r, r + 1, true);
+      halo_prefetch(r + 1);
+    }
+    for (int y = ys; y < ye; y++) {
+      const bool more = (y + 1 < ye);
+      halo_row(y + 1, y + 2, more);
+      block_sync();
+      if (more) halo_prefetch(y + 2);   // lands while the body warps run phase 2
+    }
+  } else {
+    // =====================================================================================
+    // body warps
+    // =====================================================================================
+    const bool need_r = active && (lane == 31 || (!FULLW && j0 + V >= ncol));
+    const bool wrap_l = active && lane == 0 && xb == 0;   // x-1 wraps to nx-1: not in the stage
+    const bool wrap_r = need_r && xb + V >= nx;           // x+4 wraps to 0
+    // obstacle bits of the thread's four cells in row r (bit 0 = the first cell): from the mask ring the
+    // stage copies fill, or (ragged widths) straight from global memory
+    auto row_bits = [&](int r) -> uint32_t {
+      if constexpr (MTMA) return mring[(r & 3) * MW + (j0 >> 5)] >> (j0 & 31);
+      else return active ? (__ldg(a.mask + (long long)r * a.mask_pitch + (xb >> 5)) >> (xb & 31)) : 0u;
+    };
+
+    auto lds4 = [&](const float* q, float (&v)[V]) {
+      const float4 f = *reinterpret_cast<const float4*>(q);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    };
+    auto st4 = [&](float* d, const float (&v)[V]) { *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]); };
+    auto cells = [&](const float (&q)[NSPEEDS][V], float l1, float l5, float l8, float r3, float r6, float r7, uint32_t bits,
+                     bool accel, float (&out)[NSPEEDS][V]) -> float {
+      if constexpr (DRY) {
+#pragma unroll
+        for (int k = 0; k < NSPEEDS; k++)
+#pragma unroll
+          for (int j = 0; j < V; j++) out[k][j] = q[k][j];
+        return l1 + r3;
+      }
+      if constexpr (PACKED) return compute_quad<JOINT>(q, l1, l5, l8, r3, r6, r7, bits, a.omega, accel, a.w1, a.w2, out);
+      else return compute_cells<V, false>(q, l1, l5, l8, r3, r6, r7, bits, a.omega, accel, a.w1, a.w2, out);
+    };
+    // Σ|u| of a row: fixed butterfly, the warp's fp32 sum added error-free to the warp's double-double of
+    // step `st` — kept in shared memory (lane 0 updates it) so that no accumulator is carried in registers
+    auto flush = [&](float& pend, int st) {
+      float t = pend;
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) t = __fadd_rn(t, __shfl_xor_sync(FULL, t, s));
+      if (lane == 0) {
+        double hi = part_hi[st][warp], lo = part_lo[st][warp];
+        dd_add(hi, lo, (double)t, 0.0);
+        part_hi[st][warp] = hi;
+        part_lo[st][warp] = lo;
+      }
+      pend = 0.0f;
+    };
+
+    // ---- phase 1: step t -> t+1 of row r: stage -> registers, count out of the stage, collide, ring stores ----
+    auto phase1 = [&](int r) -> float {
+      mbar_wait(full, parity);               // the stage holds row r's inputs
+      parity ^= 1;
+      // reads are unconditional: every index lies inside the row buffers, and what inactive
+      // lanes (columns beyond a ragged strip) compute from it is never stored or summed
+      float q[NSPEEDS][V];
+#pragma unroll
+      for (int k = 0; k < NSPEEDS; k++) lds4(stage + k * RS + c, q[k]);
+      float f1 = 0.f, f5 = 0.f, f8 = 0.f, f3 = 0.f, f6 = 0.f, f7 = 0.f;
+      if (lane == 0) { f1 = stage[1 * RS + c - 1]; f5 = stage[5 * RS + c - 1]; f8 = stage[8 * RS + c - 1]; }
+      if (need_r) { f3 = stage[3 * RS + c + V]; f6 = stage[6 * RS + c + V]; f7 = stage[7 * RS + c + V]; }
+      if (wrap_l) { f1 = wst[3]; f5 = wst[7]; f8 = wst[11]; }      // the stage holds the wrong row there
+      if (wrap_r) { f3 = wst[12]; f6 = wst[16]; f7 = wst[20]; }
+      const uint32_t bits = row_bits(r);
+      stage_consumed();                      // the halo warp requests row next_r's copies from here on
+
+      const bool accel = (global_row(r, fa.y0, fa.ny) == accel_g);   // the second step always follows
+      float l1 = __shfl_up_sync(FULL, q[1][V - 1], 1);
+      float l5 = __shfl_up_sync(FULL, q[5][V - 1], 1);
+      float l8 = __shfl_up_sync(FULL, q[8][V - 1], 1);
+      float r3 = __shfl_down_sync(FULL, q[3][0], 1);
+      float r6 = __shfl_down_sync(FULL, q[6][0], 1);
+      float r7 = __shfl_down_sync(FULL, q[7][0], 1);
+      if (lane == 0) { l1 = f1; l5 = f5; l8 = f8; }
+      if (need_r) { r3 = f3; r6 = f6; r7 = f7; }
+      float out[NSPEEDS][V];
+      float tot = cells(q, l1, l5, l8, r3, r6, r7, bits, accel, out);
+      if (active) {
+        float* n = rn(r) + c;
+        float* m = rm(r) + c;
+        float* so = rs(r) + c;
+        st4(m + 0 * RS, out[0]); st4(m + 1 * RS, out[1]); st4(m + 2 * RS, out[3]);
+        st4(so + 0 * RS, out[2]); st4(so + 1 * RS, out[5]); st4(so + 2 * RS, out[6]);
+        st4(n + 0 * RS, out[4]); st4(n + 1 * RS, out[7]); st4(n + 2 * RS, out[8]);
+      } else {
+        tot = 0.0f;
+      }
+      return tot;
+    };
+
+    // ---- phase 2: step t+1 -> t+2 of row y, inputs from the ring; returns the thread's Σ|u| ----
+    auto phase2 = [&](int y) -> float {
+      const float* m = rm(y) + c;        // planes 0,1,3 of row y
+      const float* so = rs(y - 1) + c;   // planes 2,5,6 of row y-1
+      const float* n = rn(y + 1) + c;    // planes 4,7,8 of row y+1
+      float g[NSPEEDS][V];
+      lds4(m + 0 * RS, g[0]); lds4(m + 1 * RS, g[1]); lds4(m + 2 * RS, g[3]);
+      lds4(so + 0 * RS, g[2]); lds4(so + 1 * RS, g[5]); lds4(so + 2 * RS, g[6]);
+      lds4(n + 0 * RS, g[4]); lds4(n + 1 * RS, g[7]); lds4(n + 2 * RS, g[8]);
+      float e1 = 0.f, e5 = 0.f, e8 = 0.f, e3 = 0.f, e6 = 0.f, e7 = 0.f;
+      if (lane == 0) { e1 = m[1 * RS - 1]; e5 = so[1 * RS - 1]; e8 = n[2 * RS - 1]; }
+      if (need_r) { e3 = m[2 * RS + V]; e6 = so[2 * RS + V]; e7 = n[1 * RS + V]; }
+      const uint32_t bits = row_bits(y);
+      float l1 = __shfl_up_sync(FULL, g[1][V - 1], 1);
+      float l5 = __shfl_up_sync(FULL, g[5][V - 1], 1);
+      float l8 = __shfl_up_sync(FULL, g[8][V - 1], 1);
+      float r3 = __shfl_down_sync(FULL, g[3][0], 1);
+      float r6 = __shfl_down_sync(FULL, g[6][0], 1);
+      float r7 = __shfl_down_sync(FULL, g[7][0], 1);
+      if (lane == 0) { l1 = e1; l5 = e5; l8 = e8; }
+      if (need_r) { r3 = e3; r6 = e6; r7 = e7; }
+
+      const bool accel = !fa.last && (global_row(y, fa.y0, fa.ny) == accel_g);
+      float out[NSPEEDS][V];
+      float tot = cells(g, l1, l5, l8, r3, r6, r7, bits, accel, out);
+      if (active) {
+        float* d = a.dst + (long long)y * a.pitch + xb;
+#pragma unroll
+        for (int k = 0; k < NSPEEDS; k++) store_vec<V, 0>(d + k * ps, out[k]);
+        if (y >= rows - 2) {   // the up neighbour's ghost rows -1, -2
+          float* gh = a.up_ghost + (long long)(y - (rows - 1)) * a.pitch + xb;
+#pragma unroll
+          for (int k = 0; k < NSPEEDS; k++) store_vec<V, 0>(gh + k * a.up_plane_stride, out[k]);
+        }
+        if (y < 2) {           // the down neighbour's ghost rows rows, rows+1
+          float* gh = a.down_ghost + (long long)y * a.pitch + xb;
+#pragma unroll
+          for (int k = 0; k < NSPEEDS; k++) store_vec<V, 0>(gh + k * a.down_plane_stride, out[k]);
+        }
+      } else {
+        tot = 0.0f;
+      }
+      return tot;
+    };
+
+    // ---- prologue: rows ys-1 and ys of step t+1 into the ring; row ys+1's inputs requested ----
+    float pend1 = 0.0f, pend2 = 0.0f;    // row sums whose butterfly is still to be done
+    for (int r = ys - 1; r <= ys; r++) {
+      const float t = phase1(r);
+      if (r == ys) {   // row ys-1 belongs to the segment below (or is a ghost row)
+        pend1 = t;
+        flush(pend1, 0);
+      }
+    }
+
+    // ---- main loop: phase 1 of row y+1, phase 2 of row y ----
+    for (int y = ys; y < ye; y++) {
+      const bool more = (y + 1 < ye);
+#ifndef LBM_F2P_NO_DEFER
+      flush(pend2, 1);                // Σ|u| of the previous iteration's phase 2
+      const float t = phase1(y + 1);
+      pend1 = more ? t : 0.0f;               // row ye belongs to the segment above (or is a ghost row)
+      block_sync();                          // rows y-1, y, y+1 of step t+1 are in the ring
+      flush(pend1, 0);
+      pend2 = phase2(y);
+#else
+      const float t = phase1(y + 1);
+      pend1 = more ? t : 0.0f;
+      flush(pend1, 0);
+      block_sync();
+      pend2 = phase2(y);
+      flush(pend2, 1);
+#endif
+    }
+    flush(pend2, 1);
+  }
+
+  if (a.edge_count != nullptr && (touches_bottom || touches_top)) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double h = 0.0, l = 0.0;
+#pragma unroll
+    for (int i = 0; i < W; i++) dd_add(h, l, part_hi[threadIdx.x][i], part_lo[threadIdx.x][i]);
+    (threadIdx.x == 0 ? fa.partials1 : fa.partials2)[blockIdx.x] = make_double2(h, l);
+  }
+  for (long long i = (long long)gridDim.x + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < fa.per_step;
+       i += (long long)gridDim.x * blockDim.x) {
+    fa.partials1[i] = make_double2(0.0, 0.0);
+    fa.partials2[i] = make_double2(0.0, 0.0);
+  }
+  if (a.edge_count != nullptr && threadIdx.x == 0) {
+    if (touches_bottom && atomicAdd(a.edge_count + 0, 1ULL) + 1ULL == a.edge_target) {
+      __threadfence_system();
+      st_release_sys(a.peer_down_flag, a.epoch);
+    }
+    if (touches_top && atomicAdd(a.edge_count + 1, 1ULL) + 1ULL == a.edge_target_top) {
+      __threadfence_system();
+      st_release_sys(a.peer_up_flag, a.epoch);
+    }
+  }
+}
+
+}  // namespace lbm

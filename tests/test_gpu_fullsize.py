@@ -49,7 +49,7 @@ def run(lbm, deck, **kw):
 def test_full_size_kernels_agree_and_conserve_mass(lbm, deck):
     p, cells, obstacles = deck
     two, av_two, info_two = run(lbm, deck)                                   # default: two-step kernel
-    assert info_two["kernel_name"].startswith("fuse2_tma_kernel")
+    assert info_two["kernel_name"].startswith("fuse2p_kernel")
     cs_two = checksum(two)
     mass0 = float(cells.sum(dtype=np.float64))
     mass1 = float(two.sum(dtype=np.float64))
@@ -71,6 +71,6 @@ def test_full_size_kernels_agree_and_conserve_mass(lbm, deck):
     del one
 
     ring, av_ring, info_ring = run(lbm, deck, devices=[0, 0])                  # two row slabs, two-step kernel
-    assert info_ring["nslabs"] == 2 and info_ring["kernel_name"].startswith("fuse2_tma_kernel")
+    assert info_ring["nslabs"] == 2 and info_ring["kernel_name"].startswith("fuse2p_kernel")
     assert checksum(ring) == cs_two
     assert np.array_equal(av_ring.view(np.uint32), av_two.view(np.uint32))

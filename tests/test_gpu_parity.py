@@ -94,9 +94,12 @@ def test_packed_and_register_bound_variants_bit_exact(lbm, oracle, tps, packed, 
 FUSE2_SHAPES = [(256, 64), (1024, 16), (100, 37), (4096, 8), (520, 40), (8, 4), (16384, 12)]
 
 
+F2_NAMES = {0: "fuse2_kernel", 1: "fuse2_tma_kernel", 2: "fuse2p_kernel"}
+
+
 @pytest.mark.parametrize("nx,ny", FUSE2_SHAPES)
 @pytest.mark.parametrize("nsteps", [8, 7])
-@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("tma", [2, 1, 0])
 def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps, tma):
     """Temporal blocking (two time steps per HBM pass, step-1 rows in a shared-memory ring) gives the
     same bits as the oracle; 7 steps = three fused pairs + one single step."""
@@ -104,7 +107,7 @@ def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps, tma):
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, nsteps, reference_order=(nx % 128 == 0))
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, nsteps,
                                       options={"persistent": 0, "fuse2": 1, "fuse2_tma": tma})
-    assert info["kernel_name"].startswith("fuse2_tma_kernel" if tma else "fuse2_kernel") and info["steps_per_launch"] == 2
+    assert info["kernel_name"].startswith(F2_NAMES[tma] + "<") and info["steps_per_launch"] == 2
     assert np.array_equal(bits(got_cells), bits(ref_cells))
     np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
 
@@ -112,7 +115,7 @@ def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps, tma):
 @pytest.mark.parametrize("warps", [2, 4, 8])
 @pytest.mark.parametrize("packed", [0, 1])
 @pytest.mark.parametrize("seg_rows", [4, 10, 256])
-@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("tma", [2, 1, 0])
 def test_two_step_kernel_variants(lbm, oracle, warps, packed, seg_rows, tma):
     """Strip width, row-segment length (redundant warm-up rows at every segment start) and packed
     arithmetic do not change a bit; av_vels equal the one-step kernel's bitwise."""
@@ -127,6 +130,47 @@ def test_two_step_kernel_variants(lbm, oracle, warps, packed, seg_rows, tma):
     assert np.array_equal(bits(got_av), bits(one_av))
 
 
+@pytest.mark.parametrize("nx,ny", [(1024, 40), (1280, 37), (100, 37), (8, 4)])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("packed", [0, 1])
+def test_repipelined_two_step_kernel(lbm, oracle, nx, ny, mode, packed):
+    """fuse2p_kernel (body warps arrive on an `empty` mbarrier once the stage is in registers, the halo
+    warp requests the next row's bulk copies; obstacle words and the periodic wrap columns travel with the
+    copies; packed reciprocal / square root with one range check per pair or per thread): full-width and
+    ragged strips, including the outermost strips' wrap; bits equal the oracle's, av_vels the one-step kernel's."""
+    p, cells, obstacles = random_case(nx, ny, seed=nx * 7 + ny, walls=False)
+    ref_cells, _ = oracle.run_f32(p, cells, obstacles, 9)
+    opts = {"persistent": 0, "fuse2": 1, "fuse2_tma": 2, "fuse2_rows": 8, "fuse2_mode": mode, "packed": packed}
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 9, options=opts)
+    assert info["kernel_name"].startswith("fuse2p_kernel<")
+    assert np.array_equal(bits(got_cells), bits(ref_cells))
+    _, one_av, _ = run_gpu(lbm, p, cells, obstacles, 9, options={"persistent": 0, "fuse2": 0, "cells_per_thread": 4})
+    assert np.array_equal(bits(got_av), bits(one_av))
+
+
+def test_fast_reciprocal_and_square_root_exhaustive(lbm):
+    """rcp_rn_fast / sqrt_rn_fast (MUFU + packed Newton step, one shared range check) return the bits of
+    __frcp_rn / __fsqrt_rn for every one of the 2^32 float bit patterns inside their range."""
+    rcp_bad, sqrt_bad = lbm.cabi.fastmath_mismatches()
+    assert (rcp_bad, sqrt_bad) == (0, 0)
+
+
+@pytest.mark.parametrize("tma", [2, 1])
+def test_two_step_kernel_cells_at_rest(lbm, oracle, tma):
+    """Exactly symmetric dyadic populations: u_sq is exactly 0 in the first step (and wherever the
+    symmetry survives), which is outside the fast square root's range — the built-in fall-back
+    must give the oracle's bits."""
+    p, cells, obstacles = random_case(1024, 24, seed=5, walls=False, perturb=0.0)
+    cells[0] = 0.5
+    cells[1:5] = 0.125
+    cells[5:9] = 0.03125
+    ref_cells, _ = oracle.run_f32(p, cells, obstacles, 4)
+    got_cells, _, info = run_gpu(lbm, p, cells, obstacles, 4,
+                                 options={"persistent": 0, "fuse2": 1, "fuse2_tma": tma, "fuse2_rows": 8})
+    assert info["kernel_name"].startswith(F2_NAMES[tma] + "<")
+    assert np.array_equal(bits(got_cells), bits(ref_cells))
+
+
 @pytest.mark.parametrize("nslabs", [2, 3])
 def test_two_step_kernel_row_slabs(lbm, nslabs):
     """Two-step kernel on a ring of slabs (two-deep ghost rows written into the neighbours, epoch flags
@@ -135,7 +179,7 @@ def test_two_step_kernel_row_slabs(lbm, nslabs):
     a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 9, options={"persistent": 0, "fuse2": 0, "cells_per_thread": 4})
     b_cells, b_av, info = run_gpu(lbm, p, cells, obstacles, 9, devices=[0] * nslabs,
                                   options={"fuse2": 1, "fuse2_rows": 8})
-    assert info["nslabs"] == nslabs and info["kernel_name"].startswith("fuse2_")
+    assert info["nslabs"] == nslabs and info["kernel_name"].startswith("fuse2")
     assert np.array_equal(bits(a_cells), bits(b_cells))
     assert np.array_equal(bits(a_av), bits(b_av))
 

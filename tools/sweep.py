@@ -33,11 +33,12 @@ def main():
     sim.upload(cells, obstacles)
     print(f"upload {time.time()-t0:.2f}s", flush=True)
     for var in args.variants.split(","):
-        if var.startswith("f2"):          # f2:<warps>:<packed>:<seg_rows>
+        if var.startswith("f2"):          # f2:<warps>:<packed>:<seg_rows>[:<prefetch>[:<kernel 0|1|2>[:<l2_ahead>[:<mode>]]]]
             _, w, pk, sr, *rest = var.split(":")
             pf = int(rest[0]) if rest else 1
             sim.set_option("fuse2_tma", int(rest[1]) if len(rest) > 1 else 1)
             sim.set_option("fuse2_l2_ahead", int(rest[2]) if len(rest) > 2 else 0)
+            sim.set_option("fuse2_mode", int(rest[3]) if len(rest) > 3 else 0)
             for k, v in (("persistent", 0), ("cells_per_thread", 4), ("fuse2", 1), ("fuse2_warps", int(w)),
                          ("packed", int(pk)), ("fuse2_rows", int(sr)), ("fuse2_prefetch", pf)):
                 sim.set_option(k, v)
@@ -45,7 +46,7 @@ def main():
             sim.sync()
             ms = sim.run_timed(args.steps)
             mlups = args.nx * args.ny * args.steps / (ms * 1e-3) / 1e6
-            print(f"{sim.info()['kernel_name']} prefetch={pf} l2_ahead={int(rest[2]) if len(rest) > 2 else 0}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
+            print(f"{var} {sim.info()['kernel_name']} prefetch={pf} l2_ahead={int(rest[2]) if len(rest) > 2 else 0}: {ms/args.steps:.4f} ms/step  {mlups:,.0f} MLUPS  "
                   f"{mlups*72/1e3:,.0f} GB/s algorithmic  {mlups*72/1e3/peak*100:.1f}% of measured HBM copy", flush=True)
             sim.set_option("fuse2", 0)
             continue
