@@ -126,6 +126,14 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
       tma_load_1d(wst + 16, ptab[6] + off + (4 - x0), 16u, full);
       tma_load_1d(wst + 20, ptab[7] + off + (4 - x0), 16u, full);
     }
+    // optional: pull the rows of iteration r + l2_ahead from HBM into L2 now, so that their bulk copies
+    // hit L2 later — more bytes in flight at the DRAM than the one stage buffer per block allows
+    const int rp = r + fa.l2_ahead;
+    if (fa.l2_ahead > 0 && rp <= ye) {
+      const long long poff = (long long)rp * a.pitch;
+#pragma unroll
+      for (int k = 0; k < NSPEEDS; k++) tma_prefetch_l2(ptab[k] + poff, RS * (uint32_t)sizeof(float));
+    }
 #pragma unroll
     for (int k = 0; k < NSPEEDS; k++) tma_load_1d(stage + k * RS, ptab[k] + off, RS * (uint32_t)sizeof(float), full);
     if constexpr (MTMA)   // the strip's obstacle words of row r: read by phase 1 of row r and, an iteration later, by phase 2

@@ -28,4 +28,4 @@ def test_ring_matches_oracle(world, ny, fuse2):
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "lattice_bit_exact=True" in proc.stdout and "av_bitwise_vs_1gpu=True" in proc.stdout
-    assert ("fuse2_tma_kernel" in proc.stdout) == bool(fuse2)
+    assert ("fuse2p_kernel" in proc.stdout) == bool(fuse2)

@@ -20,7 +20,15 @@ KEEP = [
     "sm__maximum_warps_per_active_cycle_pct", "launch__registers_per_thread", "launch__occupancy_limit_registers",
     "launch__waves_per_multiprocessor", "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.sum",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_shared_mem",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
     "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio",
     "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio",
 ]
@@ -97,7 +105,7 @@ def main():
     name = kname
     if m:
         name = f"step_kernel<V={m.group(1)},hint={m.group(2)},tpb={m.group(3)},tps={m.group(4)},packed={m.group(5)}>"
-    m = re.search(r"(fuse2_tma_kernel|fuse2_kernel)<(\d+), (\d+)", kname)
+    m = re.search(r"(fuse2p_kernel|fuse2_tma_kernel|fuse2_kernel)<(\d+), (\d+)", kname)
     if m:
         steps = 2
         rows = sys.argv[4] if len(sys.argv) > 4 else "128"
