@@ -40,6 +40,14 @@ constexpr int fuse2p_smem_bytes() {
   return (27 + NSPEEDS) * (128 * W + 8) * (int)sizeof(float) + 24 + NSPEEDS * 8 + 4 * 4 * W * (int)sizeof(uint32_t) + 6 * 4 * (int)sizeof(float);
 }
 
+// one lane of a converged warp; ptxas then knows the thread is unique and moves the bulk-copy operands to
+// uniform registers directly (a plain `lane == 0` gets a ~13-instruction uniformisation loop per copy)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
   auto rs = [&](int r) { return ring_s + (r & 3) * (3 * RS); };
 
   uint32_t parity = 0;
-  if (threadIdx.x == 0) issue_row(ys - 1);
+  if (warp == 0 && elect_one()) issue_row(ys - 1);
 
   if (halo_warp) {
     // =====================================================================================
@@ -203,12 +211,20 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
         ht[7] = stage[7 * RS + hidx + 1];
         ht[8] = stage[8 * RS + hidx - 1];
       }
+      const bool accel = (global_row(r, fa.y0, fa.ny) == accel_g);
+      const bool hfluid = ((hmask >> (xh & 31)) & 1u) == 0u;
+      float o[NSPEEDS];
       if (hl) {
-        const bool accel = (global_row(r, fa.y0, fa.ny) == accel_g);
-        const bool hfluid = ((hmask >> (xh & 31)) & 1u) == 0u;
-        float o[NSPEEDS];
-        collide_cell(ht, hfluid, a.omega, o);
+        collide_cell(ht, hfluid, a.omega, o);   // (consumes the stage values: they are in registers from here on)
         if (accel) accelerate_cell(o, hfluid, a.w1, a.w2);
+      }
+      __syncwarp();
+      if (more) {   // the body warps have read their share of the stage: request the next row
+        mbar_wait(empty, eparity);
+        if (elect_one()) issue_row(next_r);
+      }
+      eparity ^= 1;
+      if (hl) {
         float* n = rn(r) + hidx;
         float* m = rm(r) + hidx;
         float* so = rs(r) + hidx;
@@ -216,11 +232,6 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
         so[0 * RS] = o[2]; so[1 * RS] = o[5]; so[2 * RS] = o[6];
         n[0 * RS] = o[4]; n[1 * RS] = o[7]; n[2 * RS] = o[8];
       }
-      if (more) {   // the halo's own stage values have been consumed above; now wait for the body warps' reads
-        mbar_wait(empty, eparity);
-        if (lane == 0) issue_row(next_r);
-      }
-      eparity ^= 1;
     };
     halo_prefetch(ys - 1);
     for (int r = ys - 1; r <= ys; r++) {
