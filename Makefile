@@ -42,8 +42,9 @@ oracle:
 run: $(EXE)
 	./$(EXE) decks/input_$(DECK).params decks/obstacles_$(DECK).dat
 
+# VELOCITY_TOLERANCE=<percent> (extension, off by default): also check the u_x, u_y, |u| columns
 check:
-	$(PYTHON) check/check.py --ref-av-vels-file=$(REF_AV_VELS_FILE) --ref-final-state-file=$(REF_FINAL_STATE_FILE) --av-vels-file=$(AV_VELS_FILE) --final-state-file=$(FINAL_STATE_FILE)
+	$(PYTHON) check/check.py --ref-av-vels-file=$(REF_AV_VELS_FILE) --ref-final-state-file=$(REF_FINAL_STATE_FILE) --av-vels-file=$(AV_VELS_FILE) --final-state-file=$(FINAL_STATE_FILE) $(if $(VELOCITY_TOLERANCE),--velocity-tolerance $(VELOCITY_TOLERANCE))
 
 # the 1024x1024 final_state golden is committed as its checked column only (90 MB as text)
 check/1024x1024.final_state.dat: check/1024x1024.final_state.pressure.npz

@@ -13,6 +13,13 @@ cannot run on an image that has only Python 3:
   * fails when the worst percentage of either file is not finite or exceeds the
     tolerance; exit status 1 on failure, 0 with "Both tests passed!" otherwise (:131-147).
 
+Extension (off by default, so the default run is the reference's check exactly):
+  * --velocity-tolerance PCT also compares the u_x, u_y and |u| columns (2, 3, 4) of final_state,
+    which the reference never looks at.  Velocities pass through zero, so the reference's
+    per-value relative measure is meaningless for them; the measure here is fp32-aware:
+    100 * |ref - sim| / max(|ref|, 1e-3 * max|ref u|), i.e. relative to the value, but never to
+    less than a thousandth of the field's largest speed.
+
 The comparison is also importable: ``compare(ref, sim)`` and ``check_files(...)``.
 """
 import argparse
@@ -34,6 +41,9 @@ def build_parser():
                         help="reference final_state results file")
     parser.add_argument("--av-vels-file", nargs=1, required=True, help="calculated av_vels results file")
     parser.add_argument("--final-state-file", nargs=1, required=True, help="calculated final_state results file")
+    parser.add_argument("--velocity-tolerance", nargs=1, default=[None], type=float,
+                        help="extension: also check the u_x, u_y, |u| columns of final_state against this "
+                             "percentage (relative to max(|ref|, 0.1 %% of the largest reference speed))")
     return parser
 
 
@@ -67,12 +77,34 @@ def compare(ref_vals, sim_vals):
     }
 
 
+def load_velocities(filename):
+    """Columns u_x, u_y, |u| of "x y u_x u_y u pressure obstacle" lines."""
+    with open(filename, "r") as fp:
+        return np.atleast_2d(np.loadtxt(fp, usecols=[2, 3, 4]))
+
+
+def compare_velocities(ref_u, sim_u):
+    """fp32-aware measure for the velocity columns: percent of max(|ref|, 1e-3 * max|ref speed|)."""
+    ref_u = np.asarray(ref_u, dtype=np.float64)
+    sim_u = np.asarray(sim_u, dtype=np.float64)
+    floor = 1e-3 * float(np.max(np.abs(ref_u[:, 2]))) if ref_u.size else 0.0
+    diff = ref_u - sim_u
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pcnt = 100.0 * np.abs(diff) / np.maximum(np.abs(ref_u), floor)
+    pcnt = np.where(np.isnan(pcnt) & (diff == 0.0), 0.0, pcnt)   # 0/0: identical zero fields
+    flat = int(np.argmax(np.where(np.isfinite(pcnt), pcnt, np.inf)))
+    row, col = divmod(flat, 3)
+    return {"row": row, "column": ("u_x", "u_y", "u")[col], "max_diff": diff[row, col], "max_diff_pcnt": pcnt[row, col],
+            "sim_val": sim_u[row, col], "ref_val": ref_u[row, col], "total": float(np.sum(np.abs(diff)))}
+
+
 def failed(diffs, tolerance):
     pct = diffs["max_diff_pcnt"]
     return (not np.isfinite(pct)) or (abs(pct) > tolerance)
 
 
-def check_files(ref_av_vels_file, ref_final_state_file, av_vels_file, final_state_file, tolerance=1.0, out=sys.stdout):
+def check_files(ref_av_vels_file, ref_final_state_file, av_vels_file, final_state_file, tolerance=1.0, out=sys.stdout,
+                velocity_tolerance=None):
     """Runs the whole check; returns the process exit status (0 pass, 1 fail)."""
     av_vels_ref = load_av_vels(ref_av_vels_file)
     final_state_ref = load_final_state(ref_final_state_file)
@@ -101,13 +133,26 @@ def check_files(ref_av_vels_file, ref_final_state_file, av_vels_file, final_stat
     print("  {sim_val:.12E} vs. {ref_val:.12E} = {max_diff_pcnt:.2g}%".format(**fs), file=out)
     print(file=out)
 
+    velocity_failed = False
+    if velocity_tolerance is not None:   # extension: the columns the reference ignores
+        uv = compare_velocities(load_velocities(ref_final_state_file), load_velocities(final_state_file))
+        uv["jj"] = int(final_state_sim[uv["row"], 0])
+        uv["ii"] = int(final_state_sim[uv["row"], 1])
+        print("Total difference in final_state velocities : {total:.12E}".format(**uv), file=out)
+        print("Biggest difference ({column} at coord ({jj:d},{ii:d})) : {max_diff:.12E}".format(**uv), file=out)
+        print("  {sim_val:.12E} vs. {ref_val:.12E} = {max_diff_pcnt:.2g}%".format(**uv), file=out)
+        print(file=out)
+        velocity_failed = failed(uv, velocity_tolerance)
+
     final_state_failed = failed(fs, tolerance)
     av_vels_failed = failed(av, tolerance)
     if final_state_failed:
         print("final state failed check", file=out)
     if av_vels_failed:
         print("av_vels failed check", file=out)
-    if final_state_failed or av_vels_failed:
+    if velocity_failed:
+        print("final state velocities failed check", file=out)
+    if final_state_failed or av_vels_failed or velocity_failed:
         return 1
     print("Both tests passed!", file=out)
     return 0
@@ -116,7 +161,8 @@ def check_files(ref_av_vels_file, ref_final_state_file, av_vels_file, final_stat
 def main(argv=None):
     args = build_parser().parse_args(argv)
     return check_files(args.ref_av_vels_file[0], args.ref_final_state_file[0], args.av_vels_file[0],
-                       args.final_state_file[0], tolerance=args.tolerance[0])
+                       args.final_state_file[0], tolerance=args.tolerance[0],
+                       velocity_tolerance=args.velocity_tolerance[0])
 
 
 if __name__ == "__main__":

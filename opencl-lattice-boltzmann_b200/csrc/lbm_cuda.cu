@@ -549,7 +549,8 @@ int launch_fuse2p_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
 }
 
 // the re-pipelined two-step kernel (lbm_fuse2p.cuh): 512-column strips.  mode bit 0: one reciprocal /
-// square-root range check per thread instead of per pair; bit 1: dry run (bandwidth experiments only)
+// square-root range check per thread instead of per pair (packed only); bit 1: dry run (bandwidth
+// experiments only)
 int launch_fuse2p(int packed, bool fullw, int mode, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
 #define F2P_(P, F)                                                                  \
   do {                                                                              \

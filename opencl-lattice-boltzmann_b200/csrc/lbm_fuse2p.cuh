@@ -389,21 +389,12 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
     // ---- main loop: phase 1 of row y+1, phase 2 of row y ----
     for (int y = ys; y < ye; y++) {
       const bool more = (y + 1 < ye);
-#ifndef LBM_F2P_NO_DEFER
       flush(pend2, 1);                // Σ|u| of the previous iteration's phase 2
       const float t = phase1(y + 1);
       pend1 = more ? t : 0.0f;               // row ye belongs to the segment above (or is a ghost row)
       block_sync();                          // rows y-1, y, y+1 of step t+1 are in the ring
       flush(pend1, 0);
       pend2 = phase2(y);
-#else
-      const float t = phase1(y + 1);
-      pend1 = more ? t : 0.0f;
-      flush(pend1, 0);
-      block_sync();
-      pend2 = phase2(y);
-      flush(pend2, 1);
-#endif
     }
     flush(pend2, 1);
   }

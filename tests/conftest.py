@@ -10,7 +10,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "slow: long CPU oracle runs, not part of the default CPU suite")
+    config.addinivalue_line("markers", "slow: long CPU oracle runs, not part of the default CPU suite "
+                                       "(LBM_RUN_SLOW=1 or -m slow runs them)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if os.environ.get("LBM_RUN_SLOW") == "1" or "slow" in (config.getoption("-m") or ""):
+        return
+    skip = pytest.mark.skip(reason="long CPU oracle run: set LBM_RUN_SLOW=1 (or -m slow)")
+    for item in items:
+        if "slow" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

@@ -80,3 +80,31 @@ def test_goldens_check_against_themselves():
     ref = (os.path.join(ROOT, "check", "128x128.av_vels.dat"), os.path.join(ROOT, "check", "128x128.final_state.dat"))
     r = run_check(ref, ref)
     assert r.returncode == 0 and "= 0%" in r.stdout
+
+
+def write_velocity_case(tmp, ux, uy, nx=4):
+    os.makedirs(tmp, exist_ok=True)
+    av_path, fs_path = os.path.join(tmp, "av.dat"), os.path.join(tmp, "fs.dat")
+    with open(av_path, "w") as fp:
+        fp.write("0:\t1.000000000000E+00\n")
+    with open(fs_path, "w") as fp:
+        for c, (a, b) in enumerate(zip(ux, uy)):
+            fp.write("%d %d %.12E %.12E %.12E %.12E %d\n" % (c % nx, c // nx, a, b, np.hypot(a, b), 0.0333, 0))
+    return av_path, fs_path
+
+
+def test_velocity_extension_is_off_by_default_and_fp32_aware(tmp_path):
+    """--velocity-tolerance also checks u_x, u_y, |u|, which the reference ignores; values
+    near zero are measured against a thousandth of the largest speed, not against themselves."""
+    ux = np.array([0.05, -0.02, 1e-9, 0.0, 0.03, 0.01, -0.04, 0.02])
+    uy = np.array([0.01, 0.00, -1e-9, 0.0, 0.02, -0.01, 0.01, 0.03])
+    ref = write_velocity_case(str(tmp_path / "r"), ux, uy)
+    # a sign flip of a 1e-9 velocity and 0.1 % noise elsewhere: fine for fp32, fatal for a naive relative measure
+    sim = write_velocity_case(str(tmp_path / "s"), ux * 1.001 * np.where(np.abs(ux) < 1e-6, -1.0, 1.0), uy * 0.999)
+    assert run_check(ref, sim).returncode == 0                       # reference behaviour: velocities not looked at
+    r = run_check(ref, sim, ["--velocity-tolerance", "1"])
+    assert r.returncode == 0 and "Total difference in final_state velocities" in r.stdout
+    bad = write_velocity_case(str(tmp_path / "b"), ux * np.where(np.arange(8) == 4, 1.05, 1.0), uy)
+    assert run_check(ref, bad).returncode == 0
+    r = run_check(ref, bad, ["--velocity-tolerance", "1"])
+    assert r.returncode == 1 and "final state velocities failed check" in r.stdout and "u_x at coord (0,1)" in r.stdout
