@@ -344,6 +344,23 @@ def run_b200_arm(args):
     if not np.isfinite(checksum):
         raise SystemExit("final state is not finite")
 
+    # ---- the kernel's own memory ceiling: the same launches without the arithmetic (LAST: it wrecks the lattice) ----
+    dry = None
+    if world == 1 and info1["kernel_name"].startswith("fuse2p_kernel") and not args.no_dry_run:
+        try:
+            sim.set_option("fuse2_mode", 3)     # bit 1: same bulk copies, ring traffic, barriers and stores, no collision
+            sim.run(4)
+            sim.sync()
+            nd = max(2, min(args.steps, 100)) & ~1
+            ms_dry = sim.run_timed(nd)
+            dry = {"mlups": round(cells_total * nd / (ms_dry * 1e-3) / 1e6, 1), "steps": nd,
+                   "frac_of_ceiling": round(mlups / (cells_total * nd / (ms_dry * 1e-3) / 1e6), 4),
+                   "note": "fuse2p_kernel with option fuse2_mode bit 1: identical memory traffic and synchronisation, "
+                           "arithmetic removed (results are garbage, measured after everything else); "
+                           "value / this = how much of the arithmetic the kernel hides behind HBM"}
+        except Exception as e:
+            dry = {"mlups": None, "note": f"failed: {e}"}
+
     sim.close()
 
     line = None
@@ -379,6 +396,7 @@ def run_b200_arm(args):
                 "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * per_gpu_cells * spl,
                 "launch_ms": round(launch_ms, 5),
                 "dram_gbs_actual": (round(traffic / (launch_ms * 1e-3) / 1e9, 1) if traffic else None),
+                "no_arithmetic_ceiling": dry,
                 "note": "per GPU; launch duration = CUDA-event time of the timed region / launches (includes 1 "
                         "accelerate pre-pass and the av_vels finalize launches). achieved = 72 B x cell updates / "
                         "time, the reference's own accounting." + (
@@ -422,6 +440,8 @@ def main():
                     help="weak (default, the driver's contract): rows-per-gpu rows on every GPU; "
                          "strong: rows-per-gpu rows in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dry-run", action="store_true",
+                    help="skip the no-arithmetic run of the two-step kernel (roofline.no_arithmetic_ceiling)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

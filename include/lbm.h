@@ -157,7 +157,8 @@ int lbm_run_timed(lbm_ctx *ctx, int nsteps, float *ms);
  * "threads_per_block", "threads_per_sm" (register bound: 512, 768, 1024), "streaming" (0: default
  * caching, 1: .cs hints), "persistent" (-1 auto, 0, 1), "global_barrier", "chunk_steps", "fuse2" (-1 auto, 0, 1: two time steps per
  * launch), "fuse2_tma" (which two-step kernel: 0 register prefetch, 1 TMA staging, 2 re-pipelined TMA
- * staging = default), "fuse2_rows", "fuse2_mode" (bit 0: one reciprocal/sqrt range check per thread; bit 1: dry run without
+ * staging = default), "fuse2_rows", "fuse2_long" (-1 auto, 0 uniform row segments, n: rows of the leading long segments),
+ * "fuse2_mode" (bit 0: one reciprocal/sqrt range check per thread; bit 1: dry run without
  * arithmetic for bandwidth experiments — garbage results).  Unknown key -> non-zero. */
 int lbm_set_option(lbm_ctx *ctx, const char *key, long value);
 int lbm_get_info(lbm_ctx *ctx, lbm_info *info);

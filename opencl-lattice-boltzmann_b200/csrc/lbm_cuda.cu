@@ -97,6 +97,7 @@ struct Slab {
   unsigned long long edge_expected = 0;      // bottom-edge completions counted so far on this slab (edge_target of the next launch)
   unsigned long long edge_expected_top = 0;  // same for the top edge
   int f2_strips = 1, f2_segs_y = 1;      // tiling of the two-step kernel
+  int f2_n_long = 0;                     // fuse2p_kernel: leading segments of f2_long rows (the rest have f2_rows)
   long long pstride = 0;                 // partial entries per step = max(step-kernel blocks, two-step blocks)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 
@@ -141,9 +142,9 @@ struct lbm_ctx {
   long long launches = 0;
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_prefetch = 1, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1;
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_prefetch = 1, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1;
   // resolved
-  int fuse2 = 0, f2_warps = 4, f2_rows = 256;
+  int fuse2 = 0, f2_warps = 4, f2_rows = 256, f2_long = 0;
   int f2_kernel = 2;           // 0: fuse2_kernel (register prefetch), 1: fuse2_tma_kernel, 2: fuse2p_kernel (W = 4 only)
   int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
   long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
@@ -239,9 +240,43 @@ void resolve_options(lbm_ctx* ctx) {
     if (ctx->packed && ctx->opt_tps != 1024) ctx->tps = 768;   // odd tail step: packed needs ~80 registers
     ctx->chunk_steps = std::max(2, ctx->chunk_steps);
     const int tx = 128 * ctx->f2_warps;
+    // fuse2p_kernel, automatic tiling: every segment start recomputes two warm-up rows (long segments are
+    // cheaper), but the launch ends when the LAST block ends (short segments leave a shorter tail), and blocks
+    // are dispatched in index order: so long segments first (2x the uniform length) and short ones (half of
+    // it) for the rows that make up the last ~two rounds of resident blocks (DESIGN.md has the measurement).
+    ctx->f2_long = 0;
     for (auto& s : ctx->slabs) {
       s.f2_strips = (nx + tx - 1) / tx;
+      s.f2_n_long = 0;
       s.f2_segs_y = (s.rows + ctx->f2_rows - 1) / ctx->f2_rows;
+    }
+    const bool forced = ctx->opt_f2_long > 0;                       // tests / sweeps: fuse2_long = rows of the long segments
+    const bool automatic = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4;
+    if (ctx->f2_kernel == 2 && (forced || automatic)) {
+      const int seg_short = forced ? ctx->f2_rows : std::max(8, ctx->f2_rows / 2);
+      const int seg_long = forced ? ctx->opt_f2_long : 2 * ctx->f2_rows;
+      int sms = 148;
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->slabs[0].device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        sms = 148;
+      }
+      // rows left to the short segments: ~two rounds of resident blocks (3 per SM); forced: a quarter of the slab
+      auto rows_short_of = [&](const Slab& s) -> long long {
+        const long long want = forced ? (s.rows + 3) / 4 : (2LL * 3 * sms + s.f2_strips - 1) / s.f2_strips * seg_short;
+        return (want + seg_short - 1) / seg_short * seg_short;
+      };
+      bool ok = true;
+      for (auto& s : ctx->slabs)
+        if (seg_long >= s.rows || (!forced && rows_short_of(s) * 2 > s.rows)) ok = false;   // small slab: stay uniform
+      if (ok) {
+        ctx->f2_long = seg_long;
+        ctx->f2_rows = seg_short;
+        for (auto& s : ctx->slabs) {
+          s.f2_n_long = (int)std::max(0LL, (s.rows - rows_short_of(s)) / seg_long);
+          const int rest = s.rows - s.f2_n_long * seg_long;
+          s.f2_segs_y = s.f2_n_long + (rest + seg_short - 1) / seg_short;
+        }
+      }
     }
   }
   for (auto& s : ctx->slabs)
@@ -729,7 +764,8 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         if (pair) {
           int top_segs = 0, bottom_segs = 0;
           for (int sy = 0; sy < s.f2_segs_y; sy++) {
-            const int ys = sy * ctx->f2_rows, ye = std::min(s.rows, ys + ctx->f2_rows);
+            int ys, ye;
+            lbm::f2_segment_rows(sy, ctx->f2_rows, ctx->f2_long, s.f2_n_long, s.rows, ys, ye);
             if (ys < 2) bottom_segs++;
             if (ye >= s.rows - 1) top_segs++;
           }
@@ -753,6 +789,8 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         fa.strips = s.f2_strips;
         fa.segs_y = s.f2_segs_y;
         fa.seg_rows = ctx->f2_rows;
+        fa.seg_long = ctx->f2_long;
+        fa.n_long = s.f2_n_long;
         fa.l2_ahead = ctx->opt_f2_l2ahead;
         fa.partials1 = s.partials + (long long)in_chunk * s.pstride;
         fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
@@ -1167,6 +1205,7 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "fuse2_rows")) ctx->opt_f2_rows = (int)value;
   else if (!strcmp(key, "fuse2_prefetch")) ctx->opt_f2_prefetch = value ? 1 : 0;
   else if (!strcmp(key, "fuse2_tma")) ctx->opt_f2_tma = (int)std::max(0L, std::min(2L, value));
+  else if (!strcmp(key, "fuse2_long")) ctx->opt_f2_long = (int)value;   // -1 auto, 0 uniform segments, n: rows of the long ones
   else if (!strcmp(key, "fuse2_mode")) ctx->opt_f2_mode = (int)(value & 3);
   else if (!strcmp(key, "fuse2_l2_ahead")) ctx->opt_f2_l2ahead = (int)std::max(0L, std::min(64L, value));
   else return fail("unknown option '%s'", key);
@@ -1242,9 +1281,14 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
     snprintf(info->kernel_name, sizeof info->kernel_name, "persistent_kernel<V=%d,tpb=%d,packed=%d>", ctx->V, ctx->tpb,
              ctx->packed);
   else if (ctx->fuse2)
-    snprintf(info->kernel_name, sizeof info->kernel_name, "%s<W=%d,packed=%d,rows=%d>",
+  {
+    char rows[16];
+    if (ctx->f2_long > 0) snprintf(rows, sizeof rows, "%d/%d", ctx->f2_long, ctx->f2_rows);   // long / short segments
+    else snprintf(rows, sizeof rows, "%d", ctx->f2_rows);
+    snprintf(info->kernel_name, sizeof info->kernel_name, "%s<W=%d,packed=%d,rows=%s>",
              ctx->f2_kernel == 2 ? "fuse2p_kernel" : ctx->f2_kernel == 1 ? "fuse2_tma_kernel" : "fuse2_kernel", ctx->f2_warps,
-             ctx->packed, ctx->f2_rows);
+             ctx->packed, rows);
+  }
   else
     snprintf(info->kernel_name, sizeof info->kernel_name, "step_kernel<V=%d,hint=%d,tpb=%d,tps=%d,packed=%d>", ctx->V,
              ctx->streaming, ctx->tpb, ctx->tps, ctx->packed);

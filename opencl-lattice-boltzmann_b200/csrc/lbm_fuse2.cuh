@@ -32,6 +32,7 @@ struct Fuse2Args {
   int strips;              // column strips of TX cells
   int segs_y;              // row segments per strip
   int seg_rows;            // rows per segment
+  int seg_long, n_long;    // fuse2p_kernel: the first n_long segments of a strip have seg_long rows (0: all seg_rows)
   int l2_ahead;            // TMA kernel: rows ahead of the stage load that are prefetched into L2 (0 = off; measured: off is best)
   double2* partials1;      // Σ|u| partials of the first step  [per_step entries, first strips*segs_y used]
   double2* partials2;      // Σ|u| partials of the second step
@@ -39,6 +40,18 @@ struct Fuse2Args {
 };
 
 constexpr int F2_RING = 4;
+
+// rows [ys, ye) of row segment sy: n_long long segments first, then segments of seg_rows rows
+__host__ __device__ inline void f2_segment_rows(int sy, int seg_rows, int seg_long, int n_long, int rows, int& ys, int& ye) {
+  if (sy < n_long) {
+    ys = sy * seg_long;
+    ye = ys + seg_long;
+  } else {
+    ys = n_long * seg_long + (sy - n_long) * seg_rows;
+    ye = ys + seg_rows;
+  }
+  if (ye > rows) ye = rows;
+}
 
 template <int W>
 constexpr int fuse2_smem_bytes() { return F2_RING * NSPEEDS * (128 * W + 8) * (int)sizeof(float); }

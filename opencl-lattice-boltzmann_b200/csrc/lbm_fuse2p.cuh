@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
     else if (b < 2 * ns) { sy = fa.segs_y - 1; strip = b - ns; }
     else { sy = 1 + (b - 2 * ns) / ns; strip = (b - 2 * ns) % ns; }
   }
-  const int ys = sy * fa.seg_rows, ye = min(rows, ys + fa.seg_rows);
+  int ys, ye;
+  f2_segment_rows(sy, fa.seg_rows, fa.seg_long, fa.n_long, rows, ys, ye);
   const int x0 = strip * TX;
   const int ncol = FULLW ? TX : min(TX, nx - x0);
   const int j0 = (warp * 32 + lane) * V;

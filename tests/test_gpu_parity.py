@@ -148,6 +148,22 @@ def test_repipelined_two_step_kernel(lbm, oracle, nx, ny, mode, packed):
     assert np.array_equal(bits(got_av), bits(one_av))
 
 
+@pytest.mark.parametrize("nx,ny,long_rows,short_rows,nslabs", [(1024, 40, 12, 4, 1), (1280, 37, 10, 8, 1), (512, 41, 6, 4, 2),
+                                                                (1024, 64, 16, 4, 3)])
+def test_two_step_kernel_two_segment_sizes(lbm, oracle, nx, ny, long_rows, short_rows, nslabs):
+    """Long row segments first, short ones for the last quarter of a slab (the automatic tiling of large slabs,
+    forced here on small ones): same bits as the oracle and as the one-step kernel, also on a ring of slabs
+    whose edge segments have different lengths."""
+    p, cells, obstacles = random_case(nx, ny, seed=nx + 3 * ny, walls=False)
+    ref_cells, _ = oracle.run_f32(p, cells, obstacles, 7)
+    opts = {"persistent": 0, "fuse2": 1, "fuse2_tma": 2, "fuse2_rows": short_rows, "fuse2_long": long_rows}
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 7, devices=[0] * nslabs, options=opts)
+    assert info["kernel_name"].startswith("fuse2p_kernel<") and f"rows={long_rows}/{short_rows}>" in info["kernel_name"]
+    assert np.array_equal(bits(got_cells), bits(ref_cells))
+    _, one_av, _ = run_gpu(lbm, p, cells, obstacles, 7, options={"persistent": 0, "fuse2": 0, "cells_per_thread": 4})
+    assert np.array_equal(bits(got_av), bits(one_av))
+
+
 def test_fast_reciprocal_and_square_root_exhaustive(lbm):
     """rcp_rn_fast / sqrt_rn_fast (MUFU + packed Newton step, one shared range check) return the bits of
     __frcp_rn / __fsqrt_rn for every one of the 2^32 float bit patterns inside their range."""

@@ -33,12 +33,13 @@ def main():
     sim.upload(cells, obstacles)
     print(f"upload {time.time()-t0:.2f}s", flush=True)
     for var in args.variants.split(","):
-        if var.startswith("f2"):          # f2:<warps>:<packed>:<seg_rows>[:<prefetch>[:<kernel 0|1|2>[:<l2_ahead>[:<mode>]]]]
+        if var.startswith("f2"):          # f2:<warps>:<packed>:<seg_rows>[:<prefetch>[:<kernel 0|1|2>[:<l2_ahead>[:<mode>[:<long_rows>]]]]]
             _, w, pk, sr, *rest = var.split(":")
             pf = int(rest[0]) if rest else 1
             sim.set_option("fuse2_tma", int(rest[1]) if len(rest) > 1 else 1)
             sim.set_option("fuse2_l2_ahead", int(rest[2]) if len(rest) > 2 else 0)
-            sim.set_option("fuse2_mode", int(rest[3]) if len(rest) > 3 else 0)
+            sim.set_option("fuse2_mode", int(rest[3]) if len(rest) > 3 else 1)
+            sim.set_option("fuse2_long", int(rest[4]) if len(rest) > 4 else 0)     # 0: uniform segments
             for k, v in (("persistent", 0), ("cells_per_thread", 4), ("fuse2", 1), ("fuse2_warps", int(w)),
                          ("packed", int(pk)), ("fuse2_rows", int(sr)), ("fuse2_prefetch", pf)):
                 sim.set_option(k, v)
