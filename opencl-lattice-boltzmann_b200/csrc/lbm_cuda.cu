@@ -251,7 +251,8 @@ void resolve_options(lbm_ctx* ctx) {
       s.f2_segs_y = (s.rows + ctx->f2_rows - 1) / ctx->f2_rows;
     }
     const bool forced = ctx->opt_f2_long > 0;                       // tests / sweeps: fuse2_long = rows of the long segments
-    const bool automatic = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4;
+    // automatic only where it was measured: slabs large enough for the 64-row uniform choice above
+    const bool automatic = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4 && ctx->f2_rows == 64;
     if (ctx->f2_kernel == 2 && (forced || automatic)) {
       const int seg_short = forced ? ctx->f2_rows : std::max(8, ctx->f2_rows / 2);
       const int seg_long = forced ? ctx->opt_f2_long : 2 * ctx->f2_rows;
