@@ -13,19 +13,26 @@
 //     the copies are in flight for a whole row time (phase 1's arithmetic + phase 2)
 //     instead of phase 2 only.  (First cut: the last warp out of the stage issued; that
 //     warp then reached the row barrier ~150 instructions late, 15 % barrier stall.);
-//   * the nine per-plane source pointers sit in a shared-memory table: issuing a row is
-//     one 64-bit add per copy;
+//   * the nine per-plane source pointers sit in a shared-memory table and the issuing lane is
+//     chosen with elect.sync, so ptxas keeps the copy operands in uniform registers: issuing
+//     a row is a handful of instructions per copy instead of a 13-instruction
+//     uniformisation loop each;
 //   * the strip's obstacle words travel with the stage copies (a tenth bulk copy of 64 bytes
 //     into a four-row ring): phase 1 and, an iteration later, phase 2 read them from shared
 //     memory — no global load, no register carried across iterations;
+//   * the periodic x wrap of the outermost strips travels with the copies too (six 16-byte
+//     bulk copies): body warps never load from global memory;
 //   * the halo warp takes its two columns from the stage (interior strips); its remaining
-//     global loads (periodic wrap, obstacle bit) are issued after the barrier, where it
+//     global loads (wrapped column, obstacle bit) are issued after the barrier, where it
 //     idles anyway;
 //   * reciprocal / square root: one range check per thread instead of one guarded
 //     region per value, Newton steps in packed FFMA2 (compute_quad, lbm_kernels.cuh);
 //   * the Σ|u| butterflies are deferred by half an iteration so their shuffle latency
-//     overlaps the other phase's arithmetic;
-//   * FULLW (nx a multiple of the strip width): no per-lane activity predicates.
+//     overlaps the other phase's arithmetic, and the double-double accumulators live in
+//     shared memory (no spill at 128 registers, 3 blocks per SM);
+//   * FULLW (nx a multiple of the strip width): no per-lane activity predicates;
+//   * row segments: long ones first, short ones for the last rounds of resident blocks
+//     (f2_segment_rows; the host picks the tiling).
 //
 // Replaces two iterations of the reference's host loop d2q9-bgk.c:221-238
 // (2 x accelerate_flow + 2 x timestep, kernels.cl:9-231).
