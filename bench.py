@@ -216,11 +216,104 @@ def run_reference_arm(args):
 # the B200 arm
 # ---------------------------------------------------------------------------------------------
 
+PREFLIGHT_ROWS = 512      # rows per rank of the N-rank parity pre-flight
+PREFLIGHT_SPLIT = (3, 4)  # two lbm_run calls: an odd tail (one-step kernel) + a split run
+
+
+def preflight_parity(lbm, torch, dist, rank, world, local_rank, barrier):
+    """N > 1 only, before anything is timed: a seeded 16384 x (512 N) ring case, 7 steps run as 3 + 4
+    (odd tail + split run) with the two-step kernel and the long/short segment tiling of the bench
+    workload, compared on rank 0 BITWISE with the CPU oracle on the whole grid (per-slab checksums of
+    the raw bits) and, for av_vels, bitwise with a single-GPU run.  The oracle is the checker here,
+    never the thing measured.  A mismatch ends the bench with a non-zero exit."""
+    import oracle_lib
+    t0 = time.time()
+    nx, R = NX, PREFLIGHT_ROWS
+    ny, y0 = R * world, rank * R
+    nsteps = sum(PREFLIGHT_SPLIT)
+    free_cells = lbm.decks.synthetic_channel_free_cells(nx, ny, walls=False)
+    p = lbm.decks.Params(nx=nx, ny=ny, maxIters=nsteps, reynolds_dim=10, density=float(np.float32(0.1)),
+                         accel=float(np.float32(0.005)), omega=float(np.float32(1.85)))
+    p.free_cells_inv = float(np.float32(1.0) / np.float32(free_cells))
+
+    def slab(y_first, rows):   # open channel (no walls: the periodic wrap carries fluid) + solid blocks
+        one = lbm.decks.Params(nx=nx, ny=rows, maxIters=0, reynolds_dim=10, density=p.density, accel=p.accel,
+                               omega=p.omega)
+        cells = lbm.decks.perturbed_rows(lbm.decks.initial_cells(one), y_first)
+        return cells, lbm.decks.synthetic_channel_rows(nx, ny, y_first, rows, walls=False)
+
+    cells, obstacles = slab(y0, R)
+    opts = {"fuse2": 1, "fuse2_rows": 32, "fuse2_long": 128}
+    sim = lbm.cabi.Simulation(p, slab=(local_rank, rank, world, y0, R), options=opts)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, sim.export_blob())
+    sim.connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+    sim.upload(cells, obstacles)
+    sim.halo_push()
+    barrier()
+    for n in PREFLIGHT_SPLIT:
+        sim.run(n)
+    sim.sync()
+    barrier()
+    got = sim.download_cells()
+    hi, lo = sim.download_av_sums(nsteps)
+    kernel = sim.info()["kernel_name"]
+    sim.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, (lbm.decks.bits_checksum(got), hi, lo))
+    result = None
+    if rank == 0:
+        full_cells, full_obst = slab(0, ny)
+        oracle_lib.build_oracle()
+        lib = oracle_lib.load("fastest")
+        lib.oracle_set_num_threads(oracle_lib.host_threads())
+        ref, ref_av = oracle_lib.run_f32(p, full_cells, full_obst, nsteps, reference_order=False, variant="fastest")
+        same = [parts[r][0] == lbm.decks.bits_checksum(ref[:, r * R:(r + 1) * R, :]) for r in range(world)]
+        av = lbm.cabi.combine_av_sums(np.stack([x[1] for x in parts]), np.stack([x[2] for x in parts]), p.free_cells_inv)
+        with lbm.cabi.Simulation(p, devices=[local_rank], options={"fuse2": 1}) as one:
+            one.upload(full_cells, full_obst)
+            for n in PREFLIGHT_SPLIT:
+                one.run(n)
+            one.sync()
+            av1 = one.download_av_vels(nsteps)
+            one_same = lbm.decks.bits_checksum(one.download_cells()) == lbm.decks.bits_checksum(ref)
+        result = {
+            "ranks": world, "grid": f"{nx}x{ny}", "rows_per_rank": R, "steps": "+".join(map(str, PREFLIGHT_SPLIT)),
+            "kernel": kernel,
+            "lattice_bit_exact": bool(all(same)),
+            "av_bitwise": bool(np.array_equal(av.view(np.uint32), av1.view(np.uint32))),
+            "av_close_to_oracle": bool(np.allclose(av, ref_av, rtol=2e-6, atol=0)),
+            "single_gpu_bit_exact": bool(one_same),
+            "checker": "oracle/lbm_oracle.c fp32 on the whole grid (per-slab checksums of the raw bits); "
+                       "av_vels vs a 1-GPU run of the same grid",
+            "seconds": None,
+        }
+        if not all(same):
+            result["slabs_differing"] = [r for r in range(world) if not same[r]]
+    ok = torch.tensor([1], device="cuda")
+    if rank == 0:
+        good = result["lattice_bit_exact"] and result["av_bitwise"] and result["av_close_to_oracle"] and \
+            result["single_gpu_bit_exact"]
+        ok[0] = 1 if good else 0
+        result["seconds"] = round(time.time() - t0, 1)
+        log(f"[parity pre-flight] {json.dumps(result)}")
+    dist.broadcast(ok, 0)
+    if int(ok.item()) != 1:
+        if rank == 0:
+            print(json.dumps({"metric": "MLUPS", "value": None, "n_gpus": world, "parity_check": result,
+                              "error": "multi-GPU parity pre-flight FAILED: nothing was timed"}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        raise SystemExit(3)
+    return result
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
 
     import opencl_lattice_boltzmann_b200 as lbm
+    from opencl_lattice_boltzmann_b200 import ring
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -242,6 +335,23 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(x):
+        if world == 1:
+            return [x]
+        out = [None] * world
+        dist.all_gather_object(out, x)
+        return out
+
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = preflight_parity(lbm, torch, dist, rank, world, local_rank, barrier)
+
     nx, rows = NX, args.rows_per_gpu
     if args.scaling == "strong":       # total work fixed: the 16384-row grid split into N slabs
         rows = args.rows_per_gpu // world
@@ -250,34 +360,49 @@ def run_b200_arm(args):
     ny_global = rows * world
     y0 = rank * rows
 
-    # ---- the deck: this rank's slab of the global synthetic channel, in pinned host memory ----
+    # ---- the deck: this rank's slab of the global synthetic channel, in pinned host memory on the GPU's NUMA node ----
     t0 = time.time()
-    free_cells = channel_free_cells(lbm, nx, ny_global)
-    p = lbm.decks.Params(nx=nx, ny=ny_global, maxIters=args.steps, reynolds_dim=10,
-                         density=float(np.float32(0.1)), accel=float(np.float32(0.005)),
-                         omega=float(np.float32(1.85)))
-    p.free_cells_inv = float(np.float32(1.0) / np.float32(free_cells))
-    cells_h = torch.empty((9, rows, nx), dtype=torch.float32, pin_memory=True)
-    obst_h = torch.empty((rows, nx), dtype=torch.int32, pin_memory=True)
+
+    def channel_params(ny, steps):
+        q = lbm.decks.Params(nx=nx, ny=ny, maxIters=steps, reynolds_dim=10, density=float(np.float32(0.1)),
+                             accel=float(np.float32(0.005)), omega=float(np.float32(1.85)))
+        q.free_cells_inv = float(np.float32(1.0) / np.float32(channel_free_cells(lbm, nx, ny)))
+        return q
+
+    p = channel_params(ny_global, args.steps)
+    pin_cells = lbm.cabi.PinnedArray((9, rows, nx), np.float32, local_rank)
+    pin_obst = lbm.cabi.PinnedArray((rows, nx), np.int32, local_rank)
+    pin_out = lbm.cabi.PinnedArray((9, rows, nx), np.float32, local_rank)
+    cells_h, obst_h, out_h = pin_cells.array, pin_obst.array, pin_out.array
     init = lbm.decks.initial_cells(lbm.decks.Params(nx=1, ny=1, maxIters=0, reynolds_dim=10, density=p.density,
                                                     accel=p.accel, omega=p.omega))
     for k in range(9):
-        cells_h[k].fill_(float(init[k, 0, 0]))
-    obst_h.copy_(torch.from_numpy(lbm.decks.synthetic_channel_rows(nx, ny_global, y0, rows)))
-    out_h = torch.empty((9, rows, nx), dtype=torch.float32, pin_memory=True)
-    log(f"[rank {rank}] deck {nx}x{rows} of {nx}x{ny_global} built in {time.time() - t0:.1f}s")
+        cells_h[k].fill(init[k, 0, 0])
+    obst_h[...] = lbm.decks.synthetic_channel_rows(nx, ny_global, y0, rows)
+    mask_h = lbm.cabi.pack_obstacles(obst_h)        # for the optional packed-mask upload (built once, outside any timing)
+    log(f"[rank {rank}] deck {nx}x{rows} of {nx}x{ny_global} built in {time.time() - t0:.1f}s "
+        f"(pinned on NUMA node {pin_cells.numa_node})")
 
     # ---- context, ring ----
-    sim = lbm.cabi.Simulation(p, slab=(local_rank, rank, world, y0, rows))
-    if world > 1:
-        blobs = [None] * world
-        dist.all_gather_object(blobs, sim.export_blob())
-        sim.connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
-
-    def upload():
-        sim.upload(cells_h, obst_h)
+    def make_sim(q, r0, nrows):
+        s = lbm.cabi.Simulation(q, slab=(local_rank, rank, world, r0, nrows))
         if world > 1:
-            sim.halo_push()
+            bl = [None] * world
+            dist.all_gather_object(bl, s.export_blob())
+            s.connect(bl[(rank - 1) % world], bl[(rank + 1) % world])
+        return s
+
+    sim = make_sim(p, y0, rows)
+
+    def upload(s=None, packed=False, c=None, o=None, m=None):
+        s = s or sim
+        c = cells_h if c is None else c
+        if packed:
+            s.upload_packed(c, mask_h if m is None else m)
+        else:
+            s.upload(c, obst_h if o is None else o)
+        if world > 1:
+            s.halo_push()
             barrier()
 
     # ---- value: lattice resident in HBM ----
@@ -294,10 +419,7 @@ def run_b200_arm(args):
     barrier()
     clocks = sampler.stop()
     info1 = sim.info()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = max_over_ranks(ms)
     cells_total = nx * ny_global
     mlups = cells_total * args.steps / (ms * 1e-3) / 1e6
     launches = int(info1["kernel_launches"] - info0["kernel_launches"])
@@ -305,46 +427,53 @@ def run_b200_arm(args):
     # per-rank av_vels -> deterministic cross-GPU combine (rank order, error-free sums)
     nav = args.warmup + args.steps
     hi, lo = sim.download_av_sums(nav)
-    if world > 1:
-        parts = [None] * world
-        dist.all_gather_object(parts, (hi, lo))
-        hi_all = np.stack([x[0] for x in parts])
-        lo_all = np.stack([x[1] for x in parts])
-    else:
-        hi_all, lo_all = hi[None], lo[None]
-    av = lbm.cabi.combine_av_sums(hi_all, lo_all, p.free_cells_inv)
+    parts = gather((hi, lo))
+    av = lbm.cabi.combine_av_sums(np.stack([x[0] for x in parts]), np.stack([x[1] for x in parts]), p.free_cells_inv)
     if not np.all(np.isfinite(av)) or not np.all(av[1:] > 0):
         raise SystemExit(f"av_vels look wrong: {av[:5]}")
 
     # ---- e2e: the reference's timed region through the C-ABI with host buffers ----
-    barrier()
-    t0 = time.perf_counter()
-    sim.upload(cells_h, obst_h)
-    if world > 1:
-        sim.halo_push()
+    def e2e_once(packed):
         barrier()
-    t_up = time.perf_counter()
-    sim.run(args.steps)
-    sim.sync()
-    t_loop = time.perf_counter()
-    sim.download_cells(out_h)
-    hi2, lo2 = sim.download_av_sums(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_parts = {"upload_s": round(t_up - t0, 4), "loop_s": round(t_loop - t_up, 4),
-                 "download_s": round(time.perf_counter() - t_loop, 4)}
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_mlups = cells_total * args.steps / e2e_s / 1e6
-    h2d = (cells_h.numel() * 4 + obst_h.numel() * 4) * world
-    d2h = (out_h.numel() * 4 + 2 * 8 * args.steps) * world
-    checksum = float(out_h[:, ::257, ::263].double().sum())
+        t_0 = time.perf_counter()
+        upload(packed=packed)
+        t_up = time.perf_counter()
+        sim.run(args.steps)
+        sim.sync()
+        t_loop = time.perf_counter()
+        sim.download_cells(out_h)
+        sim.download_av_sums(args.steps)
+        t_down = time.perf_counter()
+        barrier()
+        total = max_over_ranks(time.perf_counter() - t_0)
+        h2d_rank = cells_h.nbytes + (mask_h.nbytes if packed else obst_h.nbytes)
+        d2h_rank = out_h.nbytes + 2 * 8 * args.steps
+        per_rank = gather((t_up - t_0, t_loop - t_up, t_down - t_loop))
+        return {
+            "value": round(cells_total * args.steps / total / 1e6, 1), "unit": "MLUPS",
+            "h2d_bytes_per_step": h2d_rank * world // args.steps, "d2h_bytes_per_step": d2h_rank * world // args.steps,
+            "seconds": round(total, 4),
+            "upload_s": round(max(x[0] for x in per_rank), 4), "loop_s": round(max(x[1] for x in per_rank), 4),
+            "download_s": round(max(x[2] for x in per_rank), 4),
+            "upload_gbs_per_rank": [round(h2d_rank / x[0] / 1e9, 1) for x in per_rank],
+            "download_gbs_per_rank": [round(d2h_rank / x[2] / 1e9, 1) for x in per_rank],
+        }
+
+    e2e = e2e_once(packed=False)
+    checksum = float(out_h[:, ::257, ::263].astype(np.float64).sum())
     if not np.isfinite(checksum):
         raise SystemExit("final state is not finite")
+    e2e["host_buffers"] = (f"cudaHostAlloc'ed on the NUMA node of each rank's GPU (lbm_host_alloc_on; nodes "
+                           f"{gather(pin_cells.numa_node)})")
+    e2e["note"] = ("one upload and one download per run as in the reference (d2q9-bgk.c:196-263), so the bytes per "
+                   "step are the run's bytes / steps; PCIe-bound for short runs.  Upload = the reference-shaped "
+                   "lbm_upload (int obstacle map, packed on the device)")
+    e2e_packed = e2e_once(packed=True)
+    e2e["with_packed_mask_upload"] = {k: e2e_packed[k] for k in ("value", "seconds", "upload_s", "h2d_bytes_per_step")}
+    e2e["with_packed_mask_upload"]["note"] = ("same region with lbm_upload_packed: the obstacle map crosses PCIe as the "
+                                              "bit mask the kernels use (1/32 of the int map), packed once by the caller")
 
-    # ---- the kernel's own memory ceiling: the same launches without the arithmetic (LAST: it wrecks the lattice) ----
+    # ---- the kernel's own memory ceiling: the same launches without the arithmetic (it wrecks the lattice) ----
     dry = None
     if world == 1 and info1["kernel_name"].startswith("fuse2p_kernel") and not args.no_dry_run:
         try:
@@ -360,8 +489,44 @@ def run_b200_arm(args):
                            "value / this = how much of the arithmetic the kernel hides behind HBM"}
         except Exception as e:
             dry = {"mlups": None, "note": f"failed: {e}"}
-
     sim.close()
+
+    # ---- strong scaling of the same 16384 x 16384 grid over the N GPUs (N > 1, weak runs only) ----
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong and args.rows_per_gpu % world == 0:
+        rows_s = args.rows_per_gpu // world
+        ny_s = args.rows_per_gpu
+        q = channel_params(ny_s, args.steps)
+        sim_s = make_sim(q, rank * rows_s, rows_s)
+        obst_s = np.ascontiguousarray(lbm.decks.synthetic_channel_rows(nx, ny_s, rank * rows_s, rows_s))
+        upload(sim_s, c=np.ascontiguousarray(cells_h[:, :rows_s, :]), o=obst_s)   # (the initial state is uniform)
+        sim_s.run(max(2, args.warmup) & ~1)
+        sim_s.sync()
+        barrier()
+        ms_s = max_over_ranks(sim_s.run_timed(args.steps))
+        barrier()
+        info_s = sim_s.info()
+        hi_s, lo_s = sim_s.download_av_sums(args.steps)
+        sim_s.close()
+        strong_mlups = nx * ny_s * args.steps / (ms_s * 1e-3) / 1e6
+        # the same grid on ONE GPU (rank 0), for the efficiency: the other ranks wait
+        n1 = None
+        if rank == 0:
+            with lbm.cabi.Simulation(q, devices=[local_rank]) as one:
+                o1 = np.ascontiguousarray(lbm.decks.synthetic_channel_rows(nx, ny_s, 0, ny_s))
+                c1 = cells_h if rows == ny_s else np.ascontiguousarray(np.broadcast_to(cells_h[:, :1, :], (9, ny_s, nx)))
+                one.upload(c1, o1)
+                one.run(max(2, args.warmup) & ~1)
+                one.sync()
+                n1 = nx * ny_s * args.steps / (one.run_timed(args.steps) * 1e-3) / 1e6
+        barrier()
+        strong = {"value": round(strong_mlups, 1), "unit": "MLUPS", "ms_per_step": round(ms_s / args.steps, 5),
+                  "grid": f"{nx}x{ny_s}", "rows_per_gpu": rows_s, "kernel": info_s["kernel_name"],
+                  "n1_value": round(n1, 1) if n1 else None,
+                  "efficiency_vs_n1": round(strong_mlups / (world * n1), 4) if n1 else None,
+                  "note": f"the {nx}x{ny_s} grid of the N = 1 bench split into {world} row slabs, {args.steps} steps, "
+                          f"CUDA events, max over ranks; n1_value = the same grid and step count on rank 0's GPU alone, "
+                          f"measured in this run"}
 
     line = None
     if rank == 0:
@@ -381,7 +546,8 @@ def run_b200_arm(args):
                 "workload": f"synthetic {nx}x{rows} channel per GPU (BASELINE.json configs[4]): "
                             f"global {nx}x{ny_global}, walls + 64x64 blocks every 1024 cells",
                 "nx": nx, "ny_global": ny_global, "rows_per_gpu": rows,
-                "decomposition": f"{world} row slab(s), one process per GPU, in-kernel halo stores over CUDA-IPC peer memory",
+                "decomposition": f"{world} row slab(s), one process per GPU, in-kernel halo stores over CUDA-IPC peer "
+                                 f"memory ({ring.halo_bytes_per_launch(nx)} B per neighbour per launch), epoch flags",
                 "kernel": kname,
                 "l2": f"no flush needed: the two lattices are {2 * 36 * per_gpu_cells / 2**30:.1f} GiB per GPU, "
                       f"far larger than the 126 MB L2",
@@ -396,24 +562,34 @@ def run_b200_arm(args):
                 "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * per_gpu_cells * spl,
                 "launch_ms": round(launch_ms, 5),
                 "dram_gbs_actual": (round(traffic / (launch_ms * 1e-3) / 1e9, 1) if traffic else None),
+                "dram_frac_of_peak": (round(traffic / (launch_ms * 1e-3) / 1e9 / peak, 4) if traffic else None),
+                "traffic_source": "profiles/step_kernel_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                  "`ncu --set full` capture of this kernel on this grid (not re-measured in this run)",
                 "no_arithmetic_ceiling": dry,
                 "note": "per GPU; launch duration = CUDA-event time of the timed region / launches (includes 1 "
                         "accelerate pre-pass and the av_vels finalize launches). achieved = 72 B x cell updates / "
                         "time, the reference's own accounting." + (
                             " frac > 1 is real work, not skipped work: this kernel advances TWO time steps per pass "
                             "over HBM (step-1 rows live in a shared-memory ring), so its DRAM traffic (`traffic`, "
-                            "ncu) is about half the algorithmic bytes and dram_gbs_actual is what HBM really "
-                            "carries; the lattice stays bit-identical to the one-step kernel and the CPU oracle "
-                            "(tests/test_gpu_parity.py)." if spl > 1 else ""),
+                            "ncu) is about half the algorithmic bytes and dram_gbs_actual / dram_frac_of_peak are what "
+                            "HBM really carries; the lattice stays bit-identical to the one-step kernel and the CPU "
+                            "oracle (tests/test_gpu_parity.py, tests/test_gpu_fullsize.py)." if spl > 1 else ""),
             },
-            "e2e": {"value": round(e2e_mlups, 1), "unit": "MLUPS", "h2d_bytes_per_step": h2d // args.steps,
-                    "d2h_bytes_per_step": d2h // args.steps, "seconds": round(e2e_s, 4), **e2e_parts,
-                    "note": "one upload and one download per run as in the reference (d2q9-bgk.c:196-263), so the "
-                            "bytes per step are the run's bytes / steps; PCIe-bound for short runs"},
+            "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
             "av_vels_last": float(av[-1]),
         }
+        if parity is not None:
+            line["parity_check"] = parity
+        if strong is not None:
+            line["strong"] = strong
+    if world == 1 and not args.no_decks:
+        try:
+            line["decks"] = decks_block(lbm, cpu=not args.no_cpu_baseline)
+        except Exception as e:
+            line["decks"] = {"error": str(e)}
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(lbm)
@@ -421,10 +597,65 @@ def run_b200_arm(args):
                 line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port",
                                         "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
+    for buf in (pin_cells, pin_obst, pin_out):
+        buf.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+DECKS = ["128x128", "128x256", "256x256", "1024x1024"]
+
+
+def decks_block(lbm, cpu=True):
+    """The four reference decks (BASELINE.json configs[0..3]) at full maxIters on cuda:0 through the C-ABI:
+    loop time by CUDA events, the reference's own timed region (d2q9-bgk.c:196-263: upload + loop + sync +
+    download) by wall clock, av_vels against the reference's golden with check.py's measure; beside it the
+    CPU oracle (all host cores) for the same deck and step count."""
+    import helpers
+    out = {}
+    for name in DECKS:
+        p, cells, obstacles = lbm.decks.load_deck(*lbm.decks.deck_paths(name))
+        n = p.maxIters
+        with lbm.cabi.Simulation(p, devices=[0]) as sim:
+            sim.upload(cells, obstacles)
+            sim.run(min(2000, n))      # warm-up (module load, clocks)
+            sim.sync()
+            sim.upload(cells, obstacles)
+            ms = sim.run_timed(n)
+            av = sim.download_av_vels(n)
+            info = sim.info()
+            t0 = time.perf_counter()   # the reference's timed region
+            sim.upload(cells, obstacles)
+            sim.run(n)
+            sim.sync()
+            sim.download_cells()
+            sim.download_av_vels(n)
+            region = time.perf_counter() - t0
+        worst, step = helpers.pct_diff(helpers.golden_av_vels(name), av)
+        rec = {"steps": n, "kernel": info["kernel_name"], "loop_s": round(ms * 1e-3, 5),
+               "us_per_step": round(ms * 1e3 / n, 4), "mlups": round(p.nx * p.ny * n / (ms * 1e-3) / 1e6, 1),
+               "timed_region_s": round(region, 5),
+               "l2_gbs_algorithmic": round(BYTES_PER_UPDATE * p.nx * p.ny * n / (ms * 1e-3) / 1e9, 1),
+               "av_vels_worst_pct_vs_golden": round(worst, 4), "passes_check_py_gate": bool(abs(worst) < 1.0)}
+        if cpu:
+            import oracle_lib
+            lib = oracle_lib.load("fastest")
+            threads = oracle_lib.host_threads()
+            lib.oracle_set_num_threads(threads)
+            t0 = time.perf_counter()
+            oracle_lib.run_f32(p, cells, obstacles, n, reference_order=False, variant="fastest")
+            cpu_s = time.perf_counter() - t0
+            rec["cpu_oracle"] = {"seconds": round(cpu_s, 3), "mlups": round(p.nx * p.ny * n / cpu_s / 1e6, 1),
+                                 "cores": threads, "kind": "port"}
+        out[name] = rec
+        log(f"[decks] {name}: {json.dumps(rec)}")
+    out["note"] = ("device loop time (CUDA events) of the full deck; l2_gbs_algorithmic = 72 B x updates / loop time (the "
+                   "lattices sit in L2; ncu's lts__t_bytes for these kernels is in profiles/); timed_region_s = upload + "
+                   "loop + sync + download by wall clock, the region the reference times (d2q9-bgk.c:196-263); "
+                   "cpu_oracle = oracle/lbm_oracle.c fp32 with OpenMP on all host cores, same deck, same steps")
+    return out
 
 
 def main():
@@ -440,6 +671,10 @@ def main():
                     help="weak (default, the driver's contract): rows-per-gpu rows on every GPU; "
                          "strong: rows-per-gpu rows in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="N > 1: skip the ring-vs-oracle bitwise pre-flight (development only)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling block")
+    ap.add_argument("--no-decks", action="store_true", help="N = 1: skip the four reference decks")
     ap.add_argument("--no-dry-run", action="store_true",
                     help="skip the no-arithmetic run of the two-step kernel (roofline.no_arithmetic_ceiling)")
     args = ap.parse_args()

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define LBM_NSPEEDS 9
-#define LBM_ABI_VERSION 1
+#define LBM_ABI_VERSION 2
 
 /* t_param, d2q9-bgk.c:81-92: same fields, same order, same types. */
 typedef struct lbm_params {
@@ -106,6 +106,15 @@ void lbm_destroy(lbm_ctx *ctx);
  * lbm_halo_push on every rank, then a host barrier. */
 int lbm_upload(lbm_ctx *ctx, const float *cells_soa, const int *obstacles);
 
+/* Same upload with the obstacle map already packed: bit (x & 31) of word
+ * [row * lbm_mask_words_per_row(nx) + (x >> 5)] is 1 for a blocked cell.  Optional fast path for
+ * callers that re-upload the same geometry (the int map is 10 % of the reference-shaped upload,
+ * d2q9-bgk.c:205-209, and is packed 32:1 on the device anyway); lbm_pack_obstacles builds the
+ * words from the reference's int map on the host. */
+int lbm_upload_packed(lbm_ctx *ctx, const float *cells_soa, const unsigned int *mask_words);
+size_t lbm_mask_words_per_row(int nx);
+void lbm_pack_obstacles(const int *obstacles, int nx, int rows, unsigned int *mask_words);
+
 /* Pushes this context's edge rows into the ring neighbours' ghost rows
  * (single-process contexts do this inside lbm_upload).  Blocking. */
 int lbm_halo_push(lbm_ctx *ctx);
@@ -132,9 +141,14 @@ int lbm_download_av_sums(lbm_ctx *ctx, double *hi, double *lo, int n);
 void lbm_combine_av_sums(const double *hi, const double *lo, int nparts, int n, int stride,
                          float free_cells_inv, float *av);
 
-/* Pinned host memory for the arrays above (optional; plain malloc works too). */
+/* Pinned host memory for the arrays above (optional; plain malloc works too).
+ * lbm_host_alloc_on places the pages on the NUMA node `device` is attached to (what makes the
+ * uploads / downloads of eight ranks on a two-socket box run at full PCIe rate each);
+ * lbm_device_numa_node reports that node (-1: unknown). */
 void *lbm_host_alloc(size_t bytes);
+void *lbm_host_alloc_on(size_t bytes, int device);
 void lbm_host_free(void *p);
+int lbm_device_numa_node(int device);
 
 /* ---- the time loop -------------------------------------------------------- */
 
@@ -144,7 +158,10 @@ void lbm_host_free(void *p);
  * Asynchronous.  In a ring every rank must call it with the same nsteps. */
 int lbm_run(lbm_ctx *ctx, int nsteps);
 
-/* Replaces clFinish (d2q9-bgk.c:239). */
+/* Replaces clFinish (d2q9-bgk.c:239).  On a ring it also reports a neighbour that never
+ * answered: the in-kernel waits are bounded (option "wait_timeout_ms", default 20 000), a
+ * timed-out wait marks the context failed and lbm_sync / the downloads return non-zero with a
+ * message — loud and fatal like checkError (d2q9-bgk.c:858-866), never a silent hang. */
 int lbm_sync(lbm_ctx *ctx);
 
 /* lbm_run + lbm_sync bracketed by CUDA events on the launching stream;
@@ -153,13 +170,17 @@ int lbm_run_timed(lbm_ctx *ctx, int nsteps, float *ms);
 
 /* ---- misc ----------------------------------------------------------------- */
 
-/* Tuning knobs, before lbm_upload: "cells_per_thread" (0 = auto, 1, 2, 4),
+/* Tuning knobs, before lbm_upload (on a multi-process ring: before lbm_export — lbm_connect
+ * compares the ranks' kernel plans and later changes are refused): "cells_per_thread" (0 = auto, 1, 2, 4),
  * "threads_per_block", "threads_per_sm" (register bound: 512, 768, 1024), "streaming" (0: default
- * caching, 1: .cs hints), "persistent" (-1 auto, 0, 1), "global_barrier", "chunk_steps", "fuse2" (-1 auto, 0, 1: two time steps per
- * launch), "fuse2_tma" (which two-step kernel: 0 register prefetch, 1 TMA staging, 2 re-pipelined TMA
- * staging = default), "fuse2_rows", "fuse2_long" (-1 auto, 0 uniform row segments, n: rows of the leading long segments),
- * "fuse2_mode" (bit 0: one reciprocal/sqrt range check per thread; bit 1: dry run without
- * arithmetic for bandwidth experiments — garbage results).  Unknown key -> non-zero. */
+ * caching, 1: .cs hints), "persistent" (-1 auto, 0, 1), "global_barrier", "chunk_steps",
+ * "tile" (-1 auto, 0, 1: the multi-step tile kernel for lattices that fit the SMs' shared memory),
+ * "tile_steps" (time steps per hand-off), "tile_w", "tile_h" (tile size), "fuse2" (-1 auto, 0, 1: two
+ * time steps per launch), "fuse2_tma" (which two-step kernel: 1 first TMA-staged version, 2 re-pipelined =
+ * default), "fuse2_rows", "fuse2_long" (-1 auto, 0 uniform row segments, n: rows of the leading long
+ * segments), "fuse2_mode" (bit 0: one reciprocal/sqrt range check per thread; bit 1: dry run without
+ * arithmetic for bandwidth experiments — garbage results), "wait_timeout_ms" (ring waits; any time).
+ * Unknown key -> non-zero. */
 int lbm_set_option(lbm_ctx *ctx, const char *key, long value);
 int lbm_get_info(lbm_ctx *ctx, lbm_info *info);
 /* Debug canary: number of non-zero floats in the pad columns [nx, pitch) of every row of both

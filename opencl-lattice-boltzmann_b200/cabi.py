@@ -20,6 +20,7 @@ EXPORTS = [
     "lbm_create", "lbm_create_on", "lbm_create_slab", "lbm_partition_rows", "lbm_export_size", "lbm_export",
     "lbm_connect", "lbm_destroy", "lbm_upload", "lbm_halo_push", "lbm_download_cells", "lbm_download_av_vels",
     "lbm_download_av_sums", "lbm_download_final_state", "lbm_combine_av_sums", "lbm_host_alloc", "lbm_host_free", "lbm_run", "lbm_sync",
+    "lbm_upload_packed", "lbm_mask_words_per_row", "lbm_pack_obstacles", "lbm_host_alloc_on", "lbm_device_numa_node",
     "lbm_run_timed", "lbm_set_option", "lbm_get_info", "lbm_debug_pad_nonzero", "lbm_debug_fastmath_mismatches", "lbm_device_count", "lbm_abi_version", "lbm_last_error",
 ]
 
@@ -69,6 +70,14 @@ def load_library(path: str | None = None):
     lib.lbm_destroy.argtypes = [vp]
     lib.lbm_destroy.restype = None
     lib.lbm_upload.argtypes = [vp, vp, vp]
+    lib.lbm_upload_packed.argtypes = [vp, vp, vp]
+    lib.lbm_mask_words_per_row.argtypes = [C.c_int]
+    lib.lbm_mask_words_per_row.restype = C.c_size_t
+    lib.lbm_pack_obstacles.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.lbm_pack_obstacles.restype = None
+    lib.lbm_host_alloc_on.argtypes = [C.c_size_t, C.c_int]
+    lib.lbm_host_alloc_on.restype = vp
+    lib.lbm_device_numa_node.argtypes = [C.c_int]
     lib.lbm_halo_push.argtypes = [vp]
     lib.lbm_download_cells.argtypes = [vp, vp]
     lib.lbm_download_av_vels.argtypes = [vp, fp, C.c_int]
@@ -132,6 +141,48 @@ def combine_av_sums(hi: np.ndarray, lo: np.ndarray, free_cells_inv: float) -> np
         H = s
         L = (L + lo[part]) + err
     return ((H + L) * np.float64(np.float32(free_cells_inv))).astype(np.float32)
+
+
+class PinnedArray:
+    """A numpy array over pinned host memory from lbm_host_alloc_on(bytes, device): pages on the NUMA
+    node the GPU is attached to.  Keep the object alive as long as `.array` is used; close() (or the
+    finaliser) returns the memory with lbm_host_free."""
+
+    def __init__(self, shape, dtype, device: int):
+        self.lib = load_library()
+        self.array = None
+        self._ptr = None
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = self.lib.lbm_host_alloc_on(max(nbytes, 1), device)
+        if not ptr:
+            raise LbmError(self.lib.lbm_last_error().decode())
+        self._ptr = ptr
+        buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self.numa_node = int(self.lib.lbm_device_numa_node(device))
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            self.lib.lbm_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pack_obstacles(obstacles: np.ndarray) -> np.ndarray:
+    """lbm_pack_obstacles: [rows, nx] int32 map -> [rows, ceil(nx/32)] uint32 bit mask (bit x&31 of word
+    x>>5 set = blocked), the layout lbm_upload_packed takes."""
+    lib = load_library()
+    obstacles = np.ascontiguousarray(obstacles, dtype=np.int32)
+    rows, nx = obstacles.shape
+    out = np.empty((rows, int(lib.lbm_mask_words_per_row(nx))), dtype=np.uint32)
+    lib.lbm_pack_obstacles(C.c_void_p(obstacles.ctypes.data), nx, rows, C.c_void_p(out.ctypes.data))
+    return out
 
 
 class Simulation:
@@ -209,6 +260,21 @@ class Simulation:
             assert cells.numel() == NSPEEDS * n and obstacles.numel() == n and cells.is_contiguous()
         self._keep = (cells, obstacles)
         self._ck(self.lib.lbm_upload(self._ctx, self._ptr(cells), self._ptr(obstacles)))
+
+    def upload_packed(self, cells, mask_words):
+        """cells as for upload(); mask_words: [rows, ceil(nx/32)] uint32 from pack_obstacles()."""
+        n = self.rows * self.params.nx
+        words = self.rows * int(self.lib.lbm_mask_words_per_row(self.params.nx))
+        if isinstance(cells, np.ndarray):
+            cells = np.ascontiguousarray(cells, dtype=np.float32)
+            assert cells.size == NSPEEDS * n
+        else:
+            assert cells.numel() == NSPEEDS * n and cells.is_contiguous()
+        if isinstance(mask_words, np.ndarray):
+            mask_words = np.ascontiguousarray(mask_words, dtype=np.uint32)
+            assert mask_words.size == words
+        self._keep = (cells, mask_words)
+        self._ck(self.lib.lbm_upload_packed(self._ctx, self._ptr(cells), self._ptr(mask_words)))
 
     def run(self, nsteps: int):
         self._ck(self.lib.lbm_run(self._ctx, nsteps))

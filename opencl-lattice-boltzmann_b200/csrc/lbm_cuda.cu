@@ -13,6 +13,9 @@
 
 #include <cuda_runtime.h>
 
+#include <sched.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -42,7 +45,23 @@ int fail(const char* fmt, ...) {
       return fail("CUDA error during '%s' on line %d: %s", #call, __LINE__, cudaGetErrorString(e_)); \
   } while (0)
 
-constexpr unsigned long long BLOB_MAGIC = 0x4c424d4232303031ULL;  // "LBMB2001"
+// Every exported call leaves the caller's current CUDA device as it found it.
+struct DeviceGuard {
+  int dev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      dev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (dev >= 0 && cudaSetDevice(dev) != cudaSuccess) (void)cudaGetLastError();
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+constexpr unsigned long long BLOB_MAGIC = 0x4c424d4232303032ULL;  // "LBMB2002"
 
 // Geometry of one slab's lattice arena, enough for a neighbour to address its
 // ghost rows, flags and obstacle mask: [buffer 0 | buffer 1 | flags | mask].
@@ -58,12 +77,21 @@ struct ArenaLayout {
   int pitch;
 };
 
+// What every rank of a ring must agree on before the first launch: the kernels wait on each
+// other's epoch flags, so a rank that picked another kernel (or another grid) would leave its
+// neighbours spinning.  Travels in the export blob; lbm_connect compares it with its own.
+struct RingPlan {
+  int nx, ny, nranks;
+  int fuse2, f2_kernel, f2_rows, f2_long, V;
+};
+
 struct Blob {
   unsigned long long magic;
   cudaIpcMemHandle_t handle;
   ArenaLayout layout;
   int device;
   int rank;
+  RingPlan plan;
 };
 
 struct Neighbour {
@@ -80,6 +108,8 @@ struct Slab {
   ArenaLayout layout{};
   uint32_t* mask = nullptr;      // row 0 of the obstacle bit mask (inside the arena; ghost rows -1 and rows)
   int* stage = nullptr;          // upload staging buffer for the obstacle ints
+  float* fs_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // output-stage staging (u_x, u_y, |u|, pressure), kept
+  long long fs_capacity = 0;     // floats per fs_stage buffer
   double2* partials = nullptr;   // chunk_steps x blocks_per_step block partials
   double2* scratch = nullptr;    // chunk_steps x splits range sums of av_finalize_kernel
   unsigned int* tickets = nullptr;
@@ -102,6 +132,7 @@ struct Slab {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 
   float* row0(int buf) const { return arena + (long long)buf * layout.buf_floats + (long long)GHOST * layout.pitch; }
+  // [0] flag_from_up, [1] flag_from_down, [2] bottom-edge count, [3] top-edge count, [4] error word
   unsigned long long* flags() const {
     return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(arena) + layout.flags_offset);
   }
@@ -135,6 +166,8 @@ struct lbm_ctx {
   bool ring = false;           // more than one slab in the whole ring -> flag protocol
   bool connected = false;
   bool uploaded = false;
+  bool failed = false;         // a ring wait timed out: the state is garbage, every later call fails
+  long wait_timeout_ms = 20000;
   int cur = 0;                 // buffer holding the current state
   unsigned long long epoch = 0;
   long long steps_done = 0;    // since creation
@@ -142,10 +175,10 @@ struct lbm_ctx {
   long long launches = 0;
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_prefetch = 1, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1;
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256, f2_long = 0;
-  int f2_kernel = 2;           // 0: fuse2_kernel (register prefetch), 1: fuse2_tma_kernel, 2: fuse2p_kernel (W = 4 only)
+  int f2_kernel = 2;           // 1: fuse2_tma_kernel (the A/B predecessor), 2: fuse2p_kernel (W = 4 only)
   int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
   long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
   float w1 = 0.f, w2 = 0.f;
@@ -198,8 +231,9 @@ void resolve_options(lbm_ctx* ctx) {
   if (tpb != 128 && tpb != 256 && tpb != 512) tpb = ctx->persistent ? 128 : 256;
   ctx->tpb = tpb;
   ctx->segs = (nx + 32 * V - 1) / (32 * V);
-  // cache-hint mode of the lattice accesses (lbm_kernels.cuh); plain ld.global.nc / st.global measured best
-  ctx->streaming = (ctx->opt_streaming == 1) ? 1 : 0;
+  // load path of the one-step kernel (lbm_kernels.cuh): ld.global.nc, or coherent ld.global.cg where ghost rows
+  // are rewritten by a neighbour while the kernel runs (every ring of several slabs) or on request
+  ctx->streaming = (ctx->opt_streaming == 1 || ctx->ring) ? 1 : 0;
   ctx->tps = (ctx->opt_tps == 768) ? 768 : 1024;
   ctx->packed = (ctx->V > 1) && (ctx->opt_packed >= 0 ? ctx->opt_packed != 0 : 0);   // refined below for fuse2
   long long per_step = 0;
@@ -218,14 +252,17 @@ void resolve_options(lbm_ctx* ctx) {
   ctx->f2_warps = (ctx->opt_f2_warps == 2 || ctx->opt_f2_warps == 4 || ctx->opt_f2_warps == 8) ? ctx->opt_f2_warps : 4;
   ctx->f2_kernel = (ctx->opt_f2_tma == 2 && ctx->f2_warps != 4) ? 1 : ctx->opt_f2_tma;   // fuse2p_kernel: 512-column strips only
   const long long total_slabs = (long long)ctx->nranks * (long long)ctx->slabs.size();
-  const bool can_fuse = !ctx->persistent && V == 4 && nx >= 8 && (ctx->p.ny / total_slabs) >= 4;
+  // the smallest slab of the even split (the same number on every rank of a ring, so all decide alike)
+  // and this context's own smallest slab (lbm_create_slab takes any row range; lbm_connect rejects a
+  // ring whose ranks planned differently)
+  long long min_rows = std::max(1LL, ctx->p.ny / total_slabs);
+  for (auto& s : ctx->slabs) min_rows = std::min<long long>(min_rows, s.rows);
+  const bool can_fuse = !ctx->persistent && V == 4 && nx >= 8 && min_rows >= 4;
   // rows per segment: every segment start recomputes two warm-up rows, so long segments are cheaper, but
   // the grid (strips x segments) should fill the ~444 resident blocks of a B200 a few times over
   {
     const long long strips = (nx + 128 * ctx->f2_warps - 1) / (128 * ctx->f2_warps);
-    // the smallest slab of the even split: the same number on every rank of a ring, so all decide alike
-    const long long min_rows = std::max(1LL, ctx->p.ny / total_slabs);
-    // measured best (tools/f2_rows_test.py): about 2048 blocks, between 16 and 64 rows per segment
+    // measured best (tools/f2_rows_sweep.py): about 2048 blocks, between 16 and 64 rows per segment
     int seg = 64;
     while (seg > 16 && min_rows * strips / seg < 2048) seg >>= 1;
     ctx->f2_rows = ctx->opt_f2_rows >= 4 ? ctx->opt_f2_rows : seg;
@@ -381,6 +418,38 @@ int wire_local_neighbours(lbm_ctx* ctx) {
   return 0;
 }
 
+RingPlan plan_of(const lbm_ctx* ctx) {
+  RingPlan pl{};
+  pl.nx = ctx->p.nx;
+  pl.ny = ctx->p.ny;
+  pl.nranks = ctx->nranks;
+  pl.fuse2 = ctx->fuse2;
+  pl.f2_kernel = ctx->fuse2 ? ctx->f2_kernel : 0;
+  pl.f2_rows = ctx->fuse2 ? ctx->f2_rows : 0;
+  pl.f2_long = ctx->fuse2 ? ctx->f2_long : 0;
+  pl.V = ctx->V;
+  return pl;
+}
+
+// A ring wait that timed out left its epoch in the slab's error word (wait_epoch, lbm_kernels.cuh).
+int check_ring_health(lbm_ctx* ctx) {
+  if (ctx->failed) return fail("the ring already failed (a neighbour did not answer); destroy the context");
+  if (!ctx->ring) return 0;
+  for (auto& s : ctx->slabs) {
+    if (set_device(s)) return 1;
+    unsigned long long word = 0;
+    CK(cudaMemcpyAsync(&word, s.flags() + 4, sizeof word, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    if (word != 0ULL) {
+      ctx->failed = true;
+      return fail("ring neighbour of rank %d (rows %d..%d) did not reach epoch %llu within %ld ms: it died, was "
+                  "launched with a different step count, or never called lbm_run; results are invalid",
+                  ctx->rank, s.y0, s.y0 + s.rows - 1, word, ctx->wait_timeout_ms);
+    }
+  }
+  return 0;
+}
+
 int create_common(lbm_ctx** out, const lbm_params* p, int nslabs, const int* devices, int rank, int nranks,
                   int y0, int rows) {
   if (!out) return fail("out is NULL");
@@ -462,7 +531,7 @@ void launch_step_h(const Variant& v, const lbm::StepArgs& a, long long blocks, c
 }
 
 void launch_step(const Variant& v, const lbm::StepArgs& a, long long blocks, cudaStream_t st) {
-  if (v.hint == 1) launch_step_h<1>(v, a, blocks, st);
+  if (v.hint) launch_step_h<5>(v, a, blocks, st);   // coherent L2 loads (rings; option streaming = 1)
   else launch_step_h<0>(v, a, blocks, st);
 }
 
@@ -526,28 +595,6 @@ int launch_persistent(const Variant& v, const lbm::PersistArgs& pa, long long gr
 #undef CALL_
 }
 
-template <int W, bool PACKED, int MINB, bool PREFETCH>
-int launch_fuse2_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
-  static bool configured[64] = {};
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
-  if (dev < 64 && !configured[dev]) {
-    CK(cudaFuncSetAttribute(lbm::fuse2_kernel<W, PACKED, MINB, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            lbm::fuse2_smem_bytes<W>()));
-    configured[dev] = true;
-  }
-  lbm::fuse2_kernel<W, PACKED, MINB, PREFETCH><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2_smem_bytes<W>(), st>>>(fa);
-  return 0;
-}
-
-template <bool PACKED, bool PREFETCH>
-int launch_fuse2_w(int warps, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
-  // resident blocks per SM the registers are bounded for: with prefetch one fewer (more live registers)
-  if (warps == 2) return launch_fuse2_t<2, PACKED, PREFETCH ? 4 : 5, PREFETCH>(fa, grid, st);
-  if (warps == 8) return launch_fuse2_t<8, PACKED, 1, PREFETCH>(fa, grid, st);
-  return launch_fuse2_t<4, PACKED, PREFETCH ? 2 : 3, PREFETCH>(fa, grid, st);
-}
-
 template <int W, bool PACKED, int MINB>
 int launch_fuse2_tma_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
   static bool configured[64] = {};
@@ -599,11 +646,6 @@ int launch_fuse2p(int packed, bool fullw, int mode, const lbm::Fuse2Args& fa, lo
 #undef F2P_
 }
 
-int launch_fuse2(int warps, int packed, int prefetch, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
-  if (packed) return prefetch ? launch_fuse2_w<true, true>(warps, fa, grid, st) : launch_fuse2_w<true, false>(warps, fa, grid, st);
-  return prefetch ? launch_fuse2_w<false, true>(warps, fa, grid, st) : launch_fuse2_w<false, false>(warps, fa, grid, st);
-}
-
 // local row of global row ny-2 in this slab, or -1
 int accel_row_of(const lbm_ctx* ctx, const Slab& s) {
   const int g = ctx->p.ny - 2;
@@ -614,6 +656,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
   if (!ctx) return fail("ctx is NULL");
   if (nsteps < 0) return fail("nsteps must be >= 0");
   if (!ctx->uploaded) return fail("lbm_run before lbm_upload");
+  if (ctx->failed) return fail("lbm_run on a failed ring (a neighbour did not answer); destroy the context");
   if (ctx->nranks > 1 && !ctx->connected) return fail("lbm_run before lbm_connect on a %d-rank ring", ctx->nranks);
   if (ms) *ms = 0.f;
   if (nsteps == 0) return 0;
@@ -760,6 +803,8 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         a.edge_count = f + 2;
         a.peer_up_flag = nb_flags(s.up) + 1;
         a.peer_down_flag = nb_flags(s.down) + 0;
+        a.error_word = f + 4;
+        a.wait_timeout_ns = (unsigned long long)std::max(1L, ctx->wait_timeout_ms) * 1000000ULL;
         // completions this launch adds to each edge counter: the warps of the two edge rows (one-step
         // kernel), or the blocks of the segments holding rows 0,1 / rows-2,rows-1 (two-step kernel)
         if (pair) {
@@ -799,9 +844,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         const long long f2grid = (long long)s.f2_strips * s.f2_segs_y;
         const int rc = ctx->f2_kernel == 2
                            ? launch_fuse2p(ctx->packed, ctx->p.nx % 512 == 0, ctx->opt_f2_mode, fa, f2grid, s.stream)
-                       : ctx->f2_kernel == 1
-                           ? launch_fuse2_tma(ctx->f2_warps, ctx->packed, fa, f2grid, s.stream)
-                           : launch_fuse2(ctx->f2_warps, ctx->packed, ctx->opt_f2_prefetch, fa, f2grid, s.stream);
+                           : launch_fuse2_tma(ctx->f2_warps, ctx->packed, fa, f2grid, s.stream);
         if (rc) return 1;
       } else {
         if (s.pstride > s.blocks)   // (tiny grids only) the step kernel writes s.blocks partials: clear the rest
@@ -902,11 +945,13 @@ void lbm_partition_rows(int ny, int nparts, int part, int* y0, int* rows) {
 int lbm_create_on(lbm_ctx** out, const lbm_params* p, int nslabs, const int* devices) {
   if (!devices) return fail("devices is NULL");
   if (validate(p)) return 1;
+  DeviceGuard guard;
   return create_common(out, p, nslabs, devices, 0, 1, 0, p->ny);
 }
 
 int lbm_create(lbm_ctx** out, const lbm_params* p, int ngpus) {
   if (validate(p)) return 1;
+  DeviceGuard guard;
   std::vector<int> devices;
   if (const char* env = getenv("LBM_DEVICES")) {
     for (const char* c = env; *c;) {
@@ -932,6 +977,7 @@ int lbm_create_slab(lbm_ctx** out, const lbm_params* p, int device, int rank, in
   if (validate(p)) return 1;
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
   if (rows < 1 || y0 < 0 || y0 + rows > p->ny) return fail("bad row range [%d, %d) of %d", y0, y0 + rows, p->ny);
+  DeviceGuard guard;
   return create_common(out, p, 1, &device, rank, nranks, y0, rows);
 }
 
@@ -940,6 +986,7 @@ size_t lbm_export_size(void) { return sizeof(Blob); }
 int lbm_export(lbm_ctx* ctx, void* blob) {
   if (!ctx || !blob) return fail("lbm_export: NULL argument");
   if (ctx->slabs.size() != 1) return fail("lbm_export needs a one-slab context (lbm_create_slab)");
+  DeviceGuard guard;
   Slab& s = ctx->slabs[0];
   if (set_device(s)) return 1;
   Blob b{};
@@ -948,6 +995,7 @@ int lbm_export(lbm_ctx* ctx, void* blob) {
   b.layout = s.layout;
   b.device = s.device;
   b.rank = ctx->rank;
+  b.plan = plan_of(ctx);
   memcpy(blob, &b, sizeof b);
   return 0;
 }
@@ -956,6 +1004,7 @@ int lbm_connect(lbm_ctx* ctx, const void* blob_down, const void* blob_up) {
   if (!ctx || !blob_down || !blob_up) return fail("lbm_connect: NULL argument");
   if (ctx->slabs.size() != 1) return fail("lbm_connect needs a one-slab context (lbm_create_slab)");
   if (ctx->nranks == 1) return 0;
+  DeviceGuard guard;
   Slab& s = ctx->slabs[0];
   if (set_device(s)) return 1;
   Blob d, u;
@@ -963,6 +1012,27 @@ int lbm_connect(lbm_ctx* ctx, const void* blob_down, const void* blob_up) {
   memcpy(&u, blob_up, sizeof u);
   if (d.magic != BLOB_MAGIC || u.magic != BLOB_MAGIC) return fail("lbm_connect: not an lbm_export blob");
   if (d.layout.pitch != ctx->pitch || u.layout.pitch != ctx->pitch) return fail("lbm_connect: neighbour pitch differs");
+  // every rank must have planned the same kernels: they wait on each other's epoch flags
+  const RingPlan mine = plan_of(ctx);
+  for (const Blob* b : {&d, &u}) {
+    const RingPlan& o = b->plan;
+    if (o.nx != mine.nx || o.ny != mine.ny || o.nranks != mine.nranks)
+      return fail("lbm_connect: rank %d describes a %dx%d grid on %d ranks, this rank %dx%d on %d", b->rank, o.nx, o.ny,
+                  o.nranks, mine.nx, mine.ny, mine.nranks);
+    if (o.fuse2 != mine.fuse2 || o.f2_kernel != mine.f2_kernel || o.f2_rows != mine.f2_rows || o.f2_long != mine.f2_long ||
+        o.V != mine.V)
+      return fail("lbm_connect: rank %d planned other kernels (two-step %d/%d rows %d/%d, %d cells per thread) than rank %d "
+                  "(two-step %d/%d rows %d/%d, %d cells per thread): give every rank the lbm_partition_rows split and "
+                  "the same options",
+                  b->rank, o.fuse2, o.f2_kernel, o.f2_long, o.f2_rows, o.V, ctx->rank, mine.fuse2, mine.f2_kernel,
+                  mine.f2_long, mine.f2_rows, mine.V);
+  }
+  // a second lbm_connect replaces the first: close what it opened
+  if (s.up.ipc && s.up.arena) CK(cudaIpcCloseMemHandle(s.up.arena));
+  if (s.down.ipc && s.down.arena) CK(cudaIpcCloseMemHandle(s.down.arena));
+  s.up = Neighbour{};
+  s.down = Neighbour{};
+  ctx->connected = false;
   void* pd = nullptr;
   CK(cudaIpcOpenMemHandle(&pd, d.handle, cudaIpcMemLazyEnablePeerAccess));
   s.down.arena = static_cast<float*>(pd);
@@ -985,6 +1055,7 @@ int lbm_connect(lbm_ctx* ctx, const void* blob_down, const void* blob_up) {
 
 void lbm_destroy(lbm_ctx* ctx) {
   if (!ctx) return;
+  DeviceGuard guard;
   for (auto& ds : ctx->streams) {
     cudaSetDevice(ds.first);
     cudaStreamSynchronize(ds.second);
@@ -995,6 +1066,8 @@ void lbm_destroy(lbm_ctx* ctx) {
     if (s.down.ipc && s.down.arena) cudaIpcCloseMemHandle(s.down.arena);
     if (s.arena) cudaFree(s.arena);
     if (s.stage) cudaFree(s.stage);
+    for (float* f : s.fs_stage)
+      if (f) cudaFree(f);
     if (s.partials) { cudaFree(s.partials); cudaFree(s.scratch); cudaFree(s.tickets); }
     if (s.progress) cudaFree(s.progress);
     if (s.av_hi) cudaFree(s.av_hi);
@@ -1010,8 +1083,14 @@ void lbm_destroy(lbm_ctx* ctx) {
   delete ctx;
 }
 
-int lbm_upload(lbm_ctx* ctx, const float* cells_soa, const int* obstacles) {
-  if (!ctx || !cells_soa || !obstacles) return fail("lbm_upload: NULL argument");
+}  // extern "C"
+
+namespace {
+
+// Uploads the lattice and the obstacle map: either the reference's int-per-cell map (packed to the
+// bit mask on the device) or an already packed mask (one 32-bit word per 32 cells of a row).
+int upload_impl(lbm_ctx* ctx, const float* cells_soa, const int* obstacles, const unsigned int* mask_words) {
+  DeviceGuard guard;
   if (sync_all(ctx)) return 1;
   resolve_options(ctx);
   for (auto& s : ctx->slabs)
@@ -1037,18 +1116,26 @@ int lbm_upload(lbm_ctx* ctx, const float* cells_soa, const int* obstacles) {
         CK(cudaMemcpy2DAsync(dst, sizeof(float) * ctx->pitch, src, sizeof(float) * nx, sizeof(float) * nx, s.rows,
                              cudaMemcpyHostToDevice, s.stream));
     }
-    // obstacle ints -> bit mask, staged through a bounded device buffer kept for later uploads; copies and
-    // pack kernels are stream-ordered, so the buffer can be reused without host synchronisation
-    const int stage_rows = (int)std::max<long long>(1, std::min<long long>(s.rows, (64LL << 20) / std::max(1, nx)));
-    if (!s.stage) CK(cudaMalloc(&s.stage, sizeof(int) * (size_t)stage_rows * nx));
-    for (int r0 = 0; r0 < s.rows; r0 += stage_rows) {
-      const int nr = std::min(stage_rows, s.rows - r0);
-      CK(cudaMemcpyAsync(s.stage, obstacles + row_off + (size_t)r0 * nx, sizeof(int) * (size_t)nr * nx,
-                         cudaMemcpyHostToDevice, s.stream));
-      dim3 grid(ctx->mask_pitch, nr);
-      lbm::pack_obstacles_kernel<<<grid, 32, 0, s.stream>>>(s.stage, nx, s.mask + (size_t)r0 * ctx->mask_pitch,
-                                                            ctx->mask_pitch);
-      ctx->launches++;
+    if (mask_words) {
+      // the device mask has the same shape (mask_pitch = ceil(nx/32) words per row): one flat copy
+      CK(cudaMemcpyAsync(s.mask, mask_words + (size_t)(s.y0 - ctx->y0) * ctx->mask_pitch,
+                         sizeof(uint32_t) * (size_t)ctx->mask_pitch * s.rows, cudaMemcpyHostToDevice, s.stream));
+    } else {
+      // obstacle ints -> bit mask, staged through a bounded device buffer kept for later uploads; copies and
+      // pack kernels are stream-ordered, so the buffer can be reused without host synchronisation
+      // (rows sit on gridDim.y: at most 65535 per launch)
+      const int stage_rows =
+          (int)std::max<long long>(1, std::min<long long>(std::min(s.rows, 65535), (64LL << 20) / std::max(1, nx)));
+      if (!s.stage) CK(cudaMalloc(&s.stage, sizeof(int) * (size_t)stage_rows * nx));
+      for (int r0 = 0; r0 < s.rows; r0 += stage_rows) {
+        const int nr = std::min(stage_rows, s.rows - r0);
+        CK(cudaMemcpyAsync(s.stage, obstacles + row_off + (size_t)r0 * nx, sizeof(int) * (size_t)nr * nx,
+                           cudaMemcpyHostToDevice, s.stream));
+        dim3 grid(ctx->mask_pitch, nr);
+        lbm::pack_obstacles_kernel<<<grid, 32, 0, s.stream>>>(s.stage, nx, s.mask + (size_t)r0 * ctx->mask_pitch,
+                                                              ctx->mask_pitch);
+        ctx->launches++;
+      }
     }
     if (s.av_hi) CK(cudaMemsetAsync(s.av_hi, 0, sizeof(double) * s.av_capacity, s.stream));
     if (s.av_lo) CK(cudaMemsetAsync(s.av_lo, 0, sizeof(double) * s.av_capacity, s.stream));
@@ -1061,16 +1148,49 @@ int lbm_upload(lbm_ctx* ctx, const float* cells_soa, const int* obstacles) {
   return 0;
 }
 
+}  // namespace
+
+extern "C" {
+
+int lbm_upload(lbm_ctx* ctx, const float* cells_soa, const int* obstacles) {
+  if (!ctx || !cells_soa || !obstacles) return fail("lbm_upload: NULL argument");
+  return upload_impl(ctx, cells_soa, obstacles, nullptr);
+}
+
+int lbm_upload_packed(lbm_ctx* ctx, const float* cells_soa, const unsigned int* mask_words) {
+  if (!ctx || !cells_soa || !mask_words) return fail("lbm_upload_packed: NULL argument");
+  return upload_impl(ctx, cells_soa, nullptr, mask_words);
+}
+
+size_t lbm_mask_words_per_row(int nx) { return (size_t)((nx + 31) / 32); }
+
+void lbm_pack_obstacles(const int* obstacles, int nx, int rows, unsigned int* mask_words) {
+  const size_t wpr = lbm_mask_words_per_row(nx);
+  for (int r = 0; r < rows; r++) {
+    const int* row = obstacles + (size_t)r * nx;
+    unsigned int* out = mask_words + (size_t)r * wpr;
+    for (size_t w = 0; w < wpr; w++) {
+      unsigned int word = 0;
+      const int x0 = (int)w * 32, n = std::min(32, nx - x0);
+      for (int b = 0; b < n; b++) word |= (row[x0 + b] != 0 ? 1u : 0u) << b;
+      out[w] = word;
+    }
+  }
+}
+
 int lbm_halo_push(lbm_ctx* ctx) {
   if (!ctx) return fail("ctx is NULL");
   if (!ctx->uploaded) return fail("lbm_halo_push before lbm_upload");
   if (ctx->nranks > 1 && !ctx->connected) return fail("lbm_halo_push before lbm_connect");
+  DeviceGuard guard;
   return push_halos(ctx);
 }
 
 int lbm_download_cells(lbm_ctx* ctx, float* cells_soa) {
   if (!ctx || !cells_soa) return fail("lbm_download_cells: NULL argument");
   if (!ctx->uploaded) return fail("lbm_download_cells before lbm_upload");
+  DeviceGuard guard;
+  if (check_ring_health(ctx)) return 1;
   const int nx = ctx->p.nx;
   const size_t host_plane = (size_t)nx * ctx->rows;
   for (auto& s : ctx->slabs) {
@@ -1092,32 +1212,40 @@ int lbm_download_cells(lbm_ctx* ctx, float* cells_soa) {
 int lbm_download_final_state(lbm_ctx* ctx, float* u_x, float* u_y, float* u, float* pressure) {
   if (!ctx) return fail("ctx is NULL");
   if (!ctx->uploaded) return fail("lbm_download_final_state before lbm_upload");
+  DeviceGuard guard;
   float* host[4] = {u_x, u_y, u, pressure};
   const int nx = ctx->p.nx;
   for (auto& s : ctx->slabs) {
     if (set_device(s)) return 1;
-    // bounded staging: at most ~64 Mi cells per field at a time
-    const int chunk = (int)std::max<long long>(1, std::min<long long>(s.rows, (64LL << 20) / std::max(1, nx)));
-    float* dev[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int f = 0; f < 4; f++)
-      if (host[f]) CK(cudaMalloc(&dev[f], sizeof(float) * (size_t)chunk * nx));
+    // bounded staging kept by the slab (freed by lbm_destroy): at most ~64 Mi cells per field at a time,
+    // and at most 65535 rows per launch (rows sit on gridDim.y); the copies are stream-ordered behind the
+    // kernel of the same chunk, so one synchronisation per slab suffices
+    const int chunk =
+        (int)std::max<long long>(1, std::min<long long>(std::min(s.rows, 65535), (64LL << 20) / std::max(1, nx)));
+    const long long need = (long long)chunk * nx;
+    for (int f = 0; f < 4; f++) {
+      if (!host[f] || (s.fs_stage[f] && s.fs_capacity >= need)) continue;
+      if (s.fs_stage[f]) CK(cudaFree(s.fs_stage[f]));
+      s.fs_stage[f] = nullptr;
+      CK(cudaMalloc(&s.fs_stage[f], sizeof(float) * (size_t)need));
+    }
+    s.fs_capacity = std::max(s.fs_capacity, need);
     for (int r0 = 0; r0 < s.rows; r0 += chunk) {
       const int nr = std::min(chunk, s.rows - r0);
       dim3 grid((nx + 255) / 256, nr);
       lbm::final_state_kernel<<<grid, 256, 0, s.stream>>>(s.row0(ctx->cur), s.layout.plane_stride, ctx->pitch, nx, r0,
-                                                          s.mask, ctx->mask_pitch, ctx->p.density, dev[0], dev[1], dev[2],
-                                                          dev[3]);
+                                                          s.mask, ctx->mask_pitch, ctx->p.density,
+                                                          host[0] ? s.fs_stage[0] : nullptr, host[1] ? s.fs_stage[1] : nullptr,
+                                                          host[2] ? s.fs_stage[2] : nullptr, host[3] ? s.fs_stage[3] : nullptr);
       ctx->launches++;
       const size_t off = ((size_t)(s.y0 - ctx->y0) + r0) * nx;
       for (int f = 0; f < 4; f++)
         if (host[f])
-          CK(cudaMemcpyAsync(host[f] + off, dev[f], sizeof(float) * (size_t)nr * nx, cudaMemcpyDeviceToHost, s.stream));
-      CK(cudaStreamSynchronize(s.stream));
+          CK(cudaMemcpyAsync(host[f] + off, s.fs_stage[f], sizeof(float) * (size_t)nr * nx, cudaMemcpyDeviceToHost, s.stream));
     }
-    for (int f = 0; f < 4; f++)
-      if (dev[f]) CK(cudaFree(dev[f]));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s.stream));
   }
-  CK(cudaGetLastError());
   return 0;
 }
 
@@ -1125,6 +1253,7 @@ int lbm_download_av_sums(lbm_ctx* ctx, double* hi, double* lo, int n) {
   if (!ctx || !hi || !lo) return fail("lbm_download_av_sums: NULL argument");
   if (n < 0 || n > ctx->steps_since_upload) return fail("asked for %d averages, %lld steps run", n, ctx->steps_since_upload);
   if (ctx->slabs.size() != 1) return fail("lbm_download_av_sums needs a one-slab context");
+  DeviceGuard guard;
   Slab& s = ctx->slabs[0];
   if (set_device(s)) return 1;
   if (n == 0) return 0;
@@ -1155,6 +1284,7 @@ int lbm_download_av_vels(lbm_ctx* ctx, float* av, int n) {
   if (ctx->nranks != 1) return fail("lbm_download_av_vels on a multi-process ring: use lbm_download_av_sums");
   if (n < 0 || n > ctx->steps_since_upload) return fail("asked for %d averages, %lld steps run", n, ctx->steps_since_upload);
   if (n == 0) return 0;
+  DeviceGuard guard;
   const int parts = (int)ctx->slabs.size();
   std::vector<double> hi((size_t)parts * n), lo((size_t)parts * n);
   for (int i = 0; i < parts; i++) {
@@ -1182,17 +1312,104 @@ void lbm_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
-int lbm_run(lbm_ctx* ctx, int nsteps) { return run_impl(ctx, nsteps, false, nullptr); }
+int lbm_device_numa_node(int device) {
+  // the PCI function's NUMA node as the kernel reports it (sysfs); -1: unknown / single node
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1;
+  }
+  for (char* c = bus; *c; c++)
+    if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* fp = fopen(path, "r");
+  if (!fp) return -1;
+  int node = -1;
+  if (fscanf(fp, "%d", &node) != 1) node = -1;
+  fclose(fp);
+  return node;
+}
 
-int lbm_run_timed(lbm_ctx* ctx, int nsteps, float* ms) { return run_impl(ctx, nsteps, true, ms); }
+void* lbm_host_alloc_on(size_t bytes, int device) {
+  // Pinned host memory on the NUMA node the GPU hangs off: on a two-socket box eight ranks moving
+  // ~20 GB each through whatever node their pages happened to land on share one socket's memory
+  // controllers and the inter-socket link (round 1: download 0.18 s on 1 GPU, 0.85 s on 8).  Linux
+  // places pages on the node of the thread that first touches them, so: bind the calling thread to
+  // the device's node, allocate + touch, restore the affinity.  No libnuma needed.
+  cpu_set_t old_set, node_set;
+  bool bound = false;
+  const int node = lbm_device_numa_node(device);
+  if (node >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0) {
+    char path[128];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    if (FILE* fp = fopen(path, "r")) {
+      CPU_ZERO(&node_set);
+      int a = 0, b = 0, n = 0;
+      while (fscanf(fp, "%d", &a) == 1) {   // "0-31,64-95"
+        b = a;
+        int c = fgetc(fp);
+        if (c == '-') {
+          if (fscanf(fp, "%d", &b) != 1) b = a;
+          c = fgetc(fp);
+        }
+        for (int i = a; i <= b && i < CPU_SETSIZE; i++)
+          if (CPU_ISSET(i, &old_set)) { CPU_SET(i, &node_set); n++; }
+        if (c != ',') break;
+      }
+      fclose(fp);
+      if (n > 0 && sched_setaffinity(0, sizeof node_set, &node_set) == 0) bound = true;
+    }
+  }
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  void* p = nullptr;
+  const bool ok = cudaSetDevice(device) == cudaSuccess && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess;
+  if (ok) {   // first touch (cudaHostAlloc has usually populated the pages already; this makes it certain)
+    volatile char* c = static_cast<volatile char*>(p);
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    for (size_t i = 0; i < bytes; i += page) c[i] = 0;
+  }
+  if (prev >= 0) (void)cudaSetDevice(prev);
+  if (bound) sched_setaffinity(0, sizeof old_set, &old_set);
+  if (!ok) {
+    (void)cudaGetLastError();
+    fail("cudaHostAlloc(%zu) for device %d failed", bytes, device);
+    return nullptr;
+  }
+  return p;
+}
+
+int lbm_run(lbm_ctx* ctx, int nsteps) {
+  DeviceGuard guard;
+  return run_impl(ctx, nsteps, false, nullptr);
+}
+
+int lbm_run_timed(lbm_ctx* ctx, int nsteps, float* ms) {
+  DeviceGuard guard;
+  if (run_impl(ctx, nsteps, true, ms)) return 1;
+  return check_ring_health(ctx);
+}
 
 int lbm_sync(lbm_ctx* ctx) {
   if (!ctx) return fail("ctx is NULL");
-  return sync_all(ctx);
+  DeviceGuard guard;
+  if (sync_all(ctx)) return 1;
+  return check_ring_health(ctx);
 }
 
 int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   if (!ctx || !key) return fail("lbm_set_option: NULL argument");
+  if (!strcmp(key, "wait_timeout_ms")) {   // not a planning option: allowed at any time
+    if (value < 1) return fail("wait_timeout_ms must be >= 1");
+    ctx->wait_timeout_ms = value;
+    return 0;
+  }
+  // everything else changes which kernels run on which grid; the ranks of a connected ring have
+  // already compared their plans (lbm_connect), so it is too late there
+  if (ctx->nranks > 1 && ctx->connected)
+    return fail("lbm_set_option('%s') after lbm_connect: set options before lbm_export on every rank", key);
+  DeviceGuard guard;
   if (!strcmp(key, "cells_per_thread")) ctx->opt_v = (int)value;
   else if (!strcmp(key, "threads_per_block")) ctx->opt_tpb = (int)value;
   else if (!strcmp(key, "streaming")) ctx->opt_streaming = (int)value;
@@ -1204,8 +1421,10 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "fuse2")) ctx->opt_fuse2 = (int)value;
   else if (!strcmp(key, "fuse2_warps")) ctx->opt_f2_warps = (int)value;
   else if (!strcmp(key, "fuse2_rows")) ctx->opt_f2_rows = (int)value;
-  else if (!strcmp(key, "fuse2_prefetch")) ctx->opt_f2_prefetch = value ? 1 : 0;
-  else if (!strcmp(key, "fuse2_tma")) ctx->opt_f2_tma = (int)std::max(0L, std::min(2L, value));
+  else if (!strcmp(key, "fuse2_tma")) {
+    if (value != 1 && value != 2) return fail("fuse2_tma must be 1 (fuse2_tma_kernel) or 2 (fuse2p_kernel)");
+    ctx->opt_f2_tma = (int)value;
+  }
   else if (!strcmp(key, "fuse2_long")) ctx->opt_f2_long = (int)value;   // -1 auto, 0 uniform segments, n: rows of the long ones
   else if (!strcmp(key, "fuse2_mode")) ctx->opt_f2_mode = (int)(value & 3);
   else if (!strcmp(key, "fuse2_l2_ahead")) ctx->opt_f2_l2ahead = (int)std::max(0L, std::min(64L, value));
@@ -1287,7 +1506,7 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
     if (ctx->f2_long > 0) snprintf(rows, sizeof rows, "%d/%d", ctx->f2_long, ctx->f2_rows);   // long / short segments
     else snprintf(rows, sizeof rows, "%d", ctx->f2_rows);
     snprintf(info->kernel_name, sizeof info->kernel_name, "%s<W=%d,packed=%d,rows=%s>",
-             ctx->f2_kernel == 2 ? "fuse2p_kernel" : ctx->f2_kernel == 1 ? "fuse2_tma_kernel" : "fuse2_kernel", ctx->f2_warps,
+             ctx->f2_kernel == 2 ? "fuse2p_kernel" : "fuse2_tma_kernel", ctx->f2_warps,
              ctx->packed, rows);
   }
   else

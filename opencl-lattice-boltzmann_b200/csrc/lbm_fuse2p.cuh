@@ -119,11 +119,15 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
   }
   if (a.edge_count != nullptr && (touches_bottom || touches_top)) {
     if (threadIdx.x == 0) {
-      if (touches_top) wait_epoch(a.flag_from_up, a.epoch - 1);
-      if (touches_bottom) wait_epoch(a.flag_from_down, a.epoch - 1);
+      if (touches_top) wait_epoch(a.flag_from_up, a.epoch - 1, a.error_word, a.wait_timeout_ns);
+      if (touches_bottom) wait_epoch(a.flag_from_down, a.epoch - 1, a.error_word, a.wait_timeout_ns);
     }
   }
   __syncthreads();
+  // ring: this block's ghost rows were written by the neighbour GPU (generic proxy, ordered by the
+  // acquire above + the barrier); the bulk copies read them through the async proxy
+  const bool ring_edge = a.edge_count != nullptr && (touches_bottom || touches_top);
+  if (ring_edge) asm volatile("fence.proxy.async.global;" ::: "memory");
 
   const int accel_g = fa.ny - 2;
 
@@ -194,15 +198,12 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
         const float* s_mid = a.src + (long long)r * a.pitch;
         const float* s_south = s_mid - a.pitch;
         const float* s_north = s_mid + a.pitch;
-        ht[0] = load_one<0>(s_mid + 0 * ps + xh);
-        ht[1] = load_one<0>(s_mid + 1 * ps + xhw);
-        ht[2] = load_one<0>(s_south + 2 * ps + xh);
-        ht[3] = load_one<0>(s_mid + 3 * ps + xhe);
-        ht[4] = load_one<0>(s_north + 4 * ps + xh);
-        ht[5] = load_one<0>(s_south + 5 * ps + xhw);
-        ht[6] = load_one<0>(s_south + 6 * ps + xhe);
-        ht[7] = load_one<0>(s_north + 7 * ps + xhe);
-        ht[8] = load_one<0>(s_north + 8 * ps + xhw);
+        // (ghost rows of a ring are rewritten during the kernel: coherent L2 loads there, never ld.global.nc)
+        const float* q[NSPEEDS] = {s_mid + 0 * ps + xh,   s_mid + 1 * ps + xhw,   s_south + 2 * ps + xh,
+                                   s_mid + 3 * ps + xhe,  s_north + 4 * ps + xh,  s_south + 5 * ps + xhw,
+                                   s_south + 6 * ps + xhe, s_north + 7 * ps + xhe, s_north + 8 * ps + xhw};
+#pragma unroll
+        for (int k = 0; k < NSPEEDS; k++) ht[k] = ring_edge ? __ldcg(q[k]) : __ldg(q[k]);
       }
     };
     auto halo_row = [&](int r, int next_r, bool more) {

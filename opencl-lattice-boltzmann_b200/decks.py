@@ -206,3 +206,25 @@ def synthetic_channel_free_cells(nx: int, ny: int, *, block=64, spacing=1024, wa
         total += rows * nx - int(synthetic_channel_rows(nx, ny, y0, rows, block=block, spacing=spacing,
                                                          walls=walls).sum(dtype=np.int64))
     return total
+
+
+def perturbed_rows(cells: np.ndarray, y0: int) -> np.ndarray:
+    """A smooth, cheap, deterministic perturbation of `cells` ([9, rows, nx], holding global rows
+    [y0, y0+rows)) in place, so that every row and column evolves differently; a function of the GLOBAL
+    cell coordinates only, so slabs built by different ranks agree with the whole grid built by one."""
+    _, rows, nx = cells.shape
+    x = np.arange(nx, dtype=np.float32)
+    y = np.arange(y0, y0 + rows, dtype=np.float32)
+    for k in range(NSPEEDS):
+        sx = np.sin(x * np.float32(0.001 * (k + 1)))
+        cy = np.cos(y * np.float32(0.0013 * (9 - k)))
+        cells[k] *= (np.float32(1.0) + np.float32(0.02) * sx[None, :] * cy[:, None]).astype(np.float32)
+    return cells
+
+
+def bits_checksum(a: np.ndarray) -> int:
+    """Order-sensitive 64-bit checksum of the raw bits of a float32 array (position-weighted sum):
+    equal checksums of two lattices = equal bits, cell for cell, for all practical purposes."""
+    v = np.ascontiguousarray(a).reshape(-1).view(np.uint32).astype(np.uint64)
+    w = (np.arange(v.size, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+    return int((v * w).sum(dtype=np.uint64))

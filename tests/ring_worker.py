@@ -26,6 +26,10 @@ def main():
     ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--split", default="11,14")  # two run() calls
     ap.add_argument("--fuse2", type=int, default=-1)
+    ap.add_argument("--absent-rank", type=int, default=-1,
+                    help="this rank never calls lbm_run: its neighbour must report a timeout, not hang")
+    ap.add_argument("--mismatch-rank", type=int, default=-1,
+                    help="this rank plans the one-step kernel, the others the two-step one: lbm_connect must refuse")
     args = ap.parse_args()
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -35,11 +39,54 @@ def main():
 
     p, cells, obstacles = helpers.random_case(args.nx, args.ny, seed=4242, walls=False)
     y0, rows = lbm.cabi.partition_rows(args.ny, world, rank)
+    fuse2 = args.fuse2
+    if args.mismatch_rank >= 0:
+        fuse2 = 0 if rank == args.mismatch_rank else 1
     sim = lbm.cabi.Simulation(p, slab=(local, rank, world, y0, rows),
-                              options={"cells_per_thread": 4, "fuse2": args.fuse2, "fuse2_rows": 8})
+                              options={"cells_per_thread": 4, "fuse2": fuse2, "fuse2_rows": 8})
     blobs = [None] * world
     dist.all_gather_object(blobs, sim.export_blob())
+    if args.mismatch_rank >= 0:
+        try:
+            sim.connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+            refused = False
+        except lbm.cabi.LbmError as e:
+            refused = "planned other kernels" in str(e)
+        flag = torch.tensor([1 if refused else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"MISMATCH_REFUSED={bool(flag.item())}", flush=True)
+        sim.close()
+        dist.destroy_process_group()
+        sys.exit(0 if flag.item() == 1 else 1)
     sim.connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+    if args.absent_rank >= 0:
+        sim.set_option("wait_timeout_ms", 1500)
+        sim.upload(np.ascontiguousarray(cells[:, y0:y0 + rows, :]), np.ascontiguousarray(obstacles[y0:y0 + rows, :]))
+        sim.halo_push()
+        torch.cuda.synchronize()
+        dist.barrier()
+        reported = True
+        if rank != args.absent_rank:
+            try:
+                sim.run(8)
+                sim.sync()
+                reported = False
+            except lbm.cabi.LbmError as e:
+                reported = "did not reach epoch" in str(e)
+            if reported:   # and the context stays failed
+                try:
+                    sim.run(1)
+                    reported = False
+                except lbm.cabi.LbmError:
+                    pass
+        flag = torch.tensor([1 if reported else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"TIMEOUT_REPORTED={bool(flag.item())}", flush=True)
+        sim.close()
+        dist.destroy_process_group()
+        sys.exit(0 if flag.item() == 1 else 1)
     sim.upload(np.ascontiguousarray(cells[:, y0:y0 + rows, :]), np.ascontiguousarray(obstacles[y0:y0 + rows, :]))
     sim.halo_push()
     torch.cuda.synchronize()

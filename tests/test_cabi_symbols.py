@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lbm):
     lib = lbm.cabi.load_library()
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.lbm_abi_version() == 1
+    assert lib.lbm_abi_version() == 2
     assert lib.lbm_export_size() > 64
 
 

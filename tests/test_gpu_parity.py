@@ -94,12 +94,12 @@ def test_packed_and_register_bound_variants_bit_exact(lbm, oracle, tps, packed, 
 FUSE2_SHAPES = [(256, 64), (1024, 16), (100, 37), (4096, 8), (520, 40), (8, 4), (16384, 12)]
 
 
-F2_NAMES = {0: "fuse2_kernel", 1: "fuse2_tma_kernel", 2: "fuse2p_kernel"}
+F2_NAMES = {1: "fuse2_tma_kernel", 2: "fuse2p_kernel"}
 
 
 @pytest.mark.parametrize("nx,ny", FUSE2_SHAPES)
 @pytest.mark.parametrize("nsteps", [8, 7])
-@pytest.mark.parametrize("tma", [2, 1, 0])
+@pytest.mark.parametrize("tma", [2, 1])
 def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps, tma):
     """Temporal blocking (two time steps per HBM pass, step-1 rows in a shared-memory ring) gives the
     same bits as the oracle; 7 steps = three fused pairs + one single step."""
@@ -115,7 +115,7 @@ def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps, tma):
 @pytest.mark.parametrize("warps", [2, 4, 8])
 @pytest.mark.parametrize("packed", [0, 1])
 @pytest.mark.parametrize("seg_rows", [4, 10, 256])
-@pytest.mark.parametrize("tma", [2, 1, 0])
+@pytest.mark.parametrize("tma", [2, 1])
 def test_two_step_kernel_variants(lbm, oracle, warps, packed, seg_rows, tma):
     """Strip width, row-segment length (redundant warm-up rows at every segment start) and packed
     arithmetic do not change a bit; av_vels equal the one-step kernel's bitwise."""
@@ -322,6 +322,74 @@ def test_final_state_fields_on_device(lbm, oracle, nx, ny, kw):
     ref = oracle.final_state_f32(p, got_cells, obstacles)
     for name, g, r in zip(("u_x", "u_y", "u", "pressure"), fields, ref):
         assert np.array_equal(bits(g), bits(r)), name
+
+
+def test_tall_narrow_grid(lbm, oracle):
+    """More than 65535 rows (the gridDim.y limit the upload's pack kernel and the output stage sit on):
+    lattice bit-exact vs the oracle, output stage bit-exact vs the host maths."""
+    p, cells, obstacles = random_case(64, 70001, seed=64)
+    ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 3)
+    with lbm.cabi.Simulation(p) as sim:
+        sim.upload(cells, obstacles)
+        sim.run(3)
+        sim.sync()
+        got_cells, got_av = sim.download_cells(), sim.download_av_vels(3)
+        fields = sim.download_final_state()
+        fields_again = sim.download_final_state()      # staging buffers are kept and reused
+    assert np.array_equal(bits(got_cells), bits(ref_cells))
+    np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
+    ref = oracle.final_state_f32(p, got_cells, obstacles)
+    for name, g, g2, r in zip(("u_x", "u_y", "u", "pressure"), fields, fields_again, ref):
+        assert np.array_equal(bits(g), bits(r)) and np.array_equal(bits(g2), bits(r)), name
+
+
+@pytest.mark.parametrize("nx,ny,kw", [(100, 37, {}), (1024, 40, {"options": {"persistent": 0, "fuse2": 1}}),
+                                      (256, 41, {"devices": [0, 0, 0]})])
+def test_upload_packed_equals_upload(lbm, nx, ny, kw):
+    """lbm_upload_packed (obstacle bit mask packed by the caller, lbm_pack_obstacles) == lbm_upload (the
+    reference-shaped int map, packed on the device): same lattice, same averages."""
+    p, cells, obstacles = random_case(nx, ny, seed=nx + ny)
+    a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 7, **kw)
+    words = lbm.cabi.pack_obstacles(obstacles)
+    assert words.shape == (ny, (nx + 31) // 32)
+    with lbm.cabi.Simulation(p, **kw) as sim:
+        sim.upload_packed(cells, words)
+        sim.run(7)
+        sim.sync()
+        b_cells, b_av = sim.download_cells(), sim.download_av_vels(7)
+    assert np.array_equal(bits(a_cells), bits(b_cells)) and np.array_equal(bits(a_av), bits(b_av))
+
+
+def test_pinned_numa_local_buffers(lbm):
+    """lbm_host_alloc_on: pinned memory usable for upload / download like any host array."""
+    p, cells, obstacles = random_case(128, 16, seed=2)
+    pc = lbm.cabi.PinnedArray(cells.shape, np.float32, 0)
+    po = lbm.cabi.PinnedArray(obstacles.shape, np.int32, 0)
+    out = lbm.cabi.PinnedArray(cells.shape, np.float32, 0)
+    pc.array[...] = cells
+    po.array[...] = obstacles
+    a_cells, _, _ = run_gpu(lbm, p, cells, obstacles, 4)
+    with lbm.cabi.Simulation(p) as sim:
+        sim.upload(pc.array, po.array)
+        sim.run(4)
+        sim.sync()
+        sim.download_cells(out.array)
+    assert np.array_equal(bits(out.array), bits(a_cells))
+    assert isinstance(pc.numa_node, int)
+    for buf in (pc, po, out):
+        buf.close()
+
+
+def test_current_device_is_left_alone(lbm):
+    """The library sets the device it needs and puts the caller's back."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs to tell devices apart")
+    torch.cuda.set_device(1)
+    p, cells, obstacles = random_case(64, 8)
+    run_gpu(lbm, p, cells, obstacles, 2, devices=[0])
+    assert torch.cuda.current_device() == 1
+    torch.cuda.set_device(0)
 
 
 def test_errors_are_loud(lbm):

@@ -189,7 +189,9 @@ def test_partition_rows_python_matches_c(lbm):
 def test_ring_neighbours_and_planes():
     assert ring.neighbours(0, 4) == (3, 1) and ring.neighbours(3, 4) == (2, 0) and ring.neighbours(0, 1) == (0, 0)
     assert ring.UP_PLANES == (2, 5, 6) and ring.DOWN_PLANES == (4, 7, 8)   # kernels.cl:106-112
-    assert ring.halo_bytes_per_step(16384) == 196608
+    assert ring.min_halo_bytes_per_step(16384) == 196608                   # 3 planes x one row
+    # what the kernels really store into each neighbour per launch: 2 ghost rows x 9 planes (csrc GHOST = 2)
+    assert ring.GHOST_ROWS == 2 and ring.halo_bytes_per_launch(16384) == 2 * 9 * 16384 * 4
 
 
 def test_combine_av_sums_is_split_invariant(lbm):
