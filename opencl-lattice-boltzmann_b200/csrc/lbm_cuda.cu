@@ -10,6 +10,7 @@
 #include "lbm_kernels.cuh"
 #include "lbm_fuse2.cuh"
 #include "lbm_fuse2p.cuh"
+#include "lbm_tile.cuh"
 
 #include <cuda_runtime.h>
 
@@ -175,11 +176,14 @@ struct lbm_ctx {
   long long launches = 0;
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1;
+      opt_tile = -1, opt_tile_steps = 0, opt_tile_w = 0, opt_tile_h = 0,
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256, f2_long = 0;
   int f2_kernel = 2;           // 1: fuse2_tma_kernel (the A/B predecessor), 2: fuse2p_kernel (W = 4 only)
   int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
+  // the multi-step tile kernel (lbm_tile.cuh): tiling of the lattice, steps per hand-off, block size
+  int tile = 0, tile_K = 4, tiles_x = 1, tiles_y = 1, tile_lw = 0, tile_lh = 0, tile_threads = 0, tile_smem = 0;
   long long per_step = 0;      // largest slab's partials per step (slab i has rows_i * segs)
   float w1 = 0.f, w2 = 0.f;
 };
@@ -210,13 +214,62 @@ int validate(const lbm_params* p) {
   return 0;
 }
 
+// Tiling for tile_kernel: at most one tile per SM, every haloed tile within one thread block
+// ((w + 2K)(h + 2K) <= 1024 threads), K <= the smallest tile's sides; among those the tiling with the
+// least work per round (the sum over the K steps of the shrinking haloed tile).  False: the lattice is
+// too large for this kernel.
+bool plan_tiles(lbm_ctx* ctx) {
+  const int nx = ctx->p.nx, ny = ctx->p.ny;
+  int sms = 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->slabs[0].device) != cudaSuccess) {
+    (void)cudaGetLastError();
+    sms = 148;
+  }
+  const int want_k = ctx->opt_tile_steps > 0 ? ctx->opt_tile_steps : 4;
+  long long best_cost = -1;
+  int best_tx = 0, best_ty = 0, best_k = 0;
+  auto consider = [&](int tx, int ty) {
+    if (tx < 1 || ty < 1 || tx > nx || ty > ny || (long long)tx * ty > sms) return;
+    const int w = (nx + tx - 1) / tx, h = (ny + ty - 1) / ty;         // largest tile
+    const int k = std::max(1, std::min(want_k, std::min(nx / tx, ny / ty)));   // <= smallest tile's sides
+    if ((long long)(w + 2 * k) * (h + 2 * k) > 1024) return;
+    long long cost = 0;
+    for (int i = 1; i <= k; i++) cost += (long long)(w + 2 * (k - i)) * (h + 2 * (k - i));
+    // cost per step (rounds of fewer steps pay the hand-off more often: weigh it like ~600 cell updates)
+    const long long per_step = (cost + 600) * 64 / k;
+    if (best_cost < 0 || per_step < best_cost || (per_step == best_cost && tx < best_tx)) {
+      best_cost = per_step; best_tx = tx; best_ty = ty; best_k = k;
+    }
+  };
+  if (ctx->opt_tile_w > 0 && ctx->opt_tile_h > 0)
+    consider((nx + ctx->opt_tile_w - 1) / ctx->opt_tile_w, (ny + ctx->opt_tile_h - 1) / ctx->opt_tile_h);
+  else
+    for (int ty = 1; ty <= std::min(ny, sms); ty++)
+      for (int tx = 1; tx <= std::min(nx, sms / ty); tx++) consider(tx, ty);
+  if (best_cost < 0) return false;
+  ctx->tiles_x = best_tx;
+  ctx->tiles_y = best_ty;
+  ctx->tile_K = best_k;
+  const int w = (nx + best_tx - 1) / best_tx, h = (ny + best_ty - 1) / best_ty;
+  ctx->tile_lw = w + 2 * best_k;
+  ctx->tile_lh = h + 2 * best_k;
+  ctx->tile_threads = std::max(64, (ctx->tile_lw * ctx->tile_lh + 31) / 32 * 32);
+  ctx->tile_smem = lbm::tile_smem_bytes(ctx->tile_lw, ctx->tile_lh, best_k, w * h);
+  return true;
+}
+
 void resolve_options(lbm_ctx* ctx) {
   const int nx = ctx->p.nx;
   // L2-resident single-slab lattices run many steps per (cooperative) launch
   const double lattice_bytes = 2.0 * 9.0 * 4.0 * (double)ctx->pitch * (double)(ctx->rows + 2 * GHOST);
   const bool can_persist = ctx->slabs.size() == 1 && ctx->nranks == 1;
-  ctx->persistent = can_persist && (ctx->opt_persistent >= 0 ? ctx->opt_persistent != 0
-                                                              : lattice_bytes <= 96.0 * 1024 * 1024);
+  // lattices small enough for the SMs' shared memory: K steps per hand-off on tiles (lbm_tile.cuh).
+  // Automatic only while "persistent" is automatic too (persistent = 0 / 1 ask for the other kernels).
+  ctx->tile = 0;
+  if (can_persist && ctx->p.ny >= 4 && (ctx->opt_tile >= 0 ? ctx->opt_tile != 0 : ctx->opt_persistent < 0))
+    ctx->tile = plan_tiles(ctx) ? 1 : 0;
+  ctx->persistent = !ctx->tile && can_persist && (ctx->opt_persistent >= 0 ? ctx->opt_persistent != 0
+                                                                           : lattice_bytes <= 96.0 * 1024 * 1024);
   int V = ctx->opt_v;
   if (V != 1 && V != 2 && V != 4) {
     V = 4;
@@ -246,6 +299,7 @@ void resolve_options(lbm_ctx* ctx) {
   ctx->per_step = per_step;
   long long chunk = ctx->opt_chunk > 0 ? ctx->opt_chunk : (64LL << 20) / (16 * std::max(1LL, per_step));
   ctx->chunk_steps = (int)std::max(1LL, std::min(chunk, 4096LL));
+  if (ctx->tile && ctx->opt_chunk <= 0) ctx->chunk_steps = 4096 / ctx->tile_K * ctx->tile_K;   // whole rounds per launch
 
   // two time steps per HBM pass (lbm_fuse2.cuh): 128-bit kernel only, lattices streamed from HBM,
   // every slab of the ring at least 4 rows (an even split, so every rank decides alike)
@@ -257,7 +311,7 @@ void resolve_options(lbm_ctx* ctx) {
   // ring whose ranks planned differently)
   long long min_rows = std::max(1LL, ctx->p.ny / total_slabs);
   for (auto& s : ctx->slabs) min_rows = std::min<long long>(min_rows, s.rows);
-  const bool can_fuse = !ctx->persistent && V == 4 && nx >= 8 && min_rows >= 4;
+  const bool can_fuse = !ctx->persistent && !ctx->tile && V == 4 && nx >= 8 && min_rows >= 4;
   // rows per segment: every segment start recomputes two warm-up rows, so long segments are cheaper, but
   // the grid (strips x segments) should fill the ~444 resident blocks of a B200 a few times over
   {
@@ -311,6 +365,8 @@ void resolve_options(lbm_ctx* ctx) {
         ctx->f2_rows = seg_short;
         for (auto& s : ctx->slabs) {
           s.f2_n_long = (int)std::max(0LL, (s.rows - rows_short_of(s)) / seg_long);
+          if (forced && ctx->opt_f2_nlong >= 0)   // sweeps: the number of long segments given outright
+            s.f2_n_long = (int)std::min<long long>(ctx->opt_f2_nlong, (s.rows - 1) / seg_long);
           const int rest = s.rows - s.f2_n_long * seg_long;
           s.f2_segs_y = s.f2_n_long + (rest + seg_short - 1) / seg_short;
         }
@@ -373,7 +429,8 @@ int ensure_partials(lbm_ctx* ctx) {
     if (s.partials) continue;
     if (set_device(s)) return 1;
     // the persistent kernel has at most one block per row, the step kernel s.blocks blocks
-    s.partial_capacity = (long long)ctx->chunk_steps * std::max<long long>(s.pstride, ctx->persistent ? s.rows : 0);
+    s.partial_capacity = (long long)ctx->chunk_steps *
+                         std::max<long long>(s.pstride, ctx->persistent ? s.rows : ctx->tile ? ctx->tiles_x * ctx->tiles_y : 0);
     CK(cudaMalloc(&s.partials, sizeof(double2) * (size_t)s.partial_capacity));
     CK(cudaMalloc(&s.scratch, sizeof(double2) * (size_t)ctx->chunk_steps * (size_t)s.splits));
     CK(cudaMalloc(&s.tickets, sizeof(unsigned int) * (size_t)ctx->chunk_steps));
@@ -699,6 +756,68 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
     }
   }
 
+  if (ctx->tile) {
+    // one cooperative launch per chunk of steps; K steps per hand-off between neighbouring tiles (lbm_tile.cuh)
+    Slab& s = ctx->slabs[0];
+    if (set_device(s)) return 1;
+    const int ntiles = ctx->tiles_x * ctx->tiles_y;
+    static bool configured[64] = {};
+    if (s.device < 64 && !configured[s.device]) {
+      CK(cudaFuncSetAttribute(lbm::tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured[s.device] = true;
+    }
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm::tile_kernel, ctx->tile_threads, ctx->tile_smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
+    if ((long long)per_sm * sms < ntiles)
+      return fail("internal: %d tiles cannot be co-resident (%d blocks per SM on %d SMs)", ntiles, per_sm, sms);
+    if (s.progress_capacity < ntiles) {
+      if (s.progress) CK(cudaFree(s.progress));
+      s.progress = nullptr;
+      CK(cudaMalloc(&s.progress, sizeof(unsigned int) * 32 * (size_t)ntiles));
+      s.progress_capacity = ntiles;
+    }
+    const long long max_steps = std::max(1LL, std::min<long long>(ctx->chunk_steps, s.partial_capacity / ntiles));
+    long long first = ctx->steps_since_upload;
+    for (int done = 0; done < nsteps;) {
+      const int n = (int)std::min<long long>(max_steps, nsteps - done);
+      lbm::TileArgs ta{};
+      ta.buf[0] = s.row0(0);
+      ta.buf[1] = s.row0(1);
+      ta.plane_stride = s.layout.plane_stride;
+      ta.pitch = ctx->pitch;
+      ta.nx = ctx->p.nx;
+      ta.ny = ctx->p.ny;
+      ta.mask = s.mask;
+      ta.mask_pitch = ctx->mask_pitch;
+      ta.omega = ctx->p.omega;
+      ta.w1 = ctx->w1;
+      ta.w2 = ctx->w2;
+      ta.tiles_x = ctx->tiles_x;
+      ta.tiles_y = ctx->tiles_y;
+      ta.K = ctx->tile_K;
+      ta.lw = ctx->tile_lw;
+      ta.lh = ctx->tile_lh;
+      ta.nsteps = n;
+      ta.first_buf = ctx->cur;
+      ta.accel_row = ctx->p.ny - 2;
+      ta.skip_last_accel = (done + n == nsteps) ? 1 : 0;
+      ta.progress = s.progress;
+      ta.partials = s.partials;
+      CK(cudaMemsetAsync(s.progress, 0, sizeof(unsigned int) * 32 * (size_t)ntiles, s.stream));
+      void* kargs[] = {&ta};
+      CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lbm::tile_kernel), dim3((unsigned)ntiles),
+                                     dim3((unsigned)ctx->tile_threads), kargs, (size_t)ctx->tile_smem, s.stream));
+      lbm::av_finalize_kernel<<<dim3(1, n), 256, 0, s.stream>>>(s.partials, ntiles, s.scratch, s.tickets, s.av_hi, s.av_lo,
+                                                                 first);
+      ctx->launches += 2;   // (+ one memset node)
+      const int rounds = (n + ctx->tile_K - 1) / ctx->tile_K;
+      ctx->cur ^= (rounds & 1);
+      first += n;
+      done += n;
+    }
+  }
+
   if (ctx->persistent) {
     // one cooperative launch per chunk of steps; grid barrier between steps (lbm_kernels.cuh)
     Slab& s = ctx->slabs[0];
@@ -769,7 +888,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
     in_chunk = 0;
     return 0;
   };
-  for (int t = 0; !ctx->persistent && t < nsteps;) {
+  for (int t = 0; !ctx->persistent && !ctx->tile && t < nsteps;) {
     const bool pair = ctx->fuse2 && (nsteps - t >= 2);   // two steps in one launch; an odd tail runs one step
     const int adv = pair ? 2 : 1;
     if (in_chunk + adv > ctx->chunk_steps && flush_chunk()) return 1;
@@ -1415,6 +1534,10 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "streaming")) ctx->opt_streaming = (int)value;
   else if (!strcmp(key, "persistent")) ctx->opt_persistent = (int)value;
   else if (!strcmp(key, "chunk_steps")) ctx->opt_chunk = (int)value;
+  else if (!strcmp(key, "tile")) ctx->opt_tile = (int)value;
+  else if (!strcmp(key, "tile_steps")) ctx->opt_tile_steps = (int)std::max(0L, std::min(64L, value));
+  else if (!strcmp(key, "tile_w")) ctx->opt_tile_w = (int)std::max(0L, value);
+  else if (!strcmp(key, "tile_h")) ctx->opt_tile_h = (int)std::max(0L, value);
   else if (!strcmp(key, "global_barrier")) ctx->opt_sync = value ? 1 : 0;
   else if (!strcmp(key, "threads_per_sm")) ctx->opt_tps = (int)value;
   else if (!strcmp(key, "packed")) ctx->opt_packed = (int)value;
@@ -1425,6 +1548,7 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
     if (value != 1 && value != 2) return fail("fuse2_tma must be 1 (fuse2_tma_kernel) or 2 (fuse2p_kernel)");
     ctx->opt_f2_tma = (int)value;
   }
+  else if (!strcmp(key, "fuse2_nlong")) ctx->opt_f2_nlong = (int)value;  // with fuse2_long > 0: how many long segments per strip
   else if (!strcmp(key, "fuse2_long")) ctx->opt_f2_long = (int)value;   // -1 auto, 0 uniform segments, n: rows of the long ones
   else if (!strcmp(key, "fuse2_mode")) ctx->opt_f2_mode = (int)(value & 3);
   else if (!strcmp(key, "fuse2_l2_ahead")) ctx->opt_f2_l2ahead = (int)std::max(0L, std::min(64L, value));
@@ -1493,11 +1617,14 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
   info->cells_per_thread = ctx->V;
   info->threads_per_block = ctx->tpb;
   info->streaming = ctx->streaming;
-  info->steps_per_launch = ctx->persistent ? ctx->chunk_steps : (ctx->fuse2 ? 2 : 1);
+  info->steps_per_launch = (ctx->persistent || ctx->tile) ? ctx->chunk_steps : (ctx->fuse2 ? 2 : 1);
   info->steps_done = ctx->steps_done;
   info->kernel_launches = ctx->launches;
   info->partials_per_step = ctx->per_step;
-  if (ctx->persistent)
+  if (ctx->tile)
+    snprintf(info->kernel_name, sizeof info->kernel_name, "tile_kernel<K=%d,tiles=%dx%d,halo=%dx%d>", ctx->tile_K,
+             ctx->tiles_x, ctx->tiles_y, ctx->tile_lw, ctx->tile_lh);
+  else if (ctx->persistent)
     snprintf(info->kernel_name, sizeof info->kernel_name, "persistent_kernel<V=%d,tpb=%d,packed=%d>", ctx->V, ctx->tpb,
              ctx->packed);
   else if (ctx->fuse2)

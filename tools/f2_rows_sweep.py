@@ -37,9 +37,11 @@ for nx, ny in shapes:
     for t in tilings:
         opts = {"fuse2": 1, "persistent": 0}
         if t != "auto":
-            if "/" in t:
-                lo, sh = t.split("/")
-                opts.update({"fuse2_long": int(lo), "fuse2_rows": int(sh)})
+            if "/" in t:     # long/short[/number of long segments per strip]
+                parts = [int(v) for v in t.split("/")]
+                opts.update({"fuse2_long": parts[0], "fuse2_rows": parts[1]})
+                if len(parts) > 2:
+                    opts["fuse2_nlong"] = parts[2]
             else:
                 opts.update({"fuse2_rows": int(t), "fuse2_long": 0})
         try:
