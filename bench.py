@@ -270,7 +270,7 @@ def preflight_parity(lbm, torch, dist, rank, world, local_rank, barrier):
         ref, ref_av = oracle_lib.run_f32(p, full_cells, full_obst, nsteps, reference_order=False, variant="fastest")
         same = [parts[r][0] == lbm.decks.bits_checksum(ref[:, r * R:(r + 1) * R, :]) for r in range(world)]
         av = lbm.cabi.combine_av_sums(np.stack([x[1] for x in parts]), np.stack([x[2] for x in parts]), p.free_cells_inv)
-        with lbm.cabi.Simulation(p, devices=[local_rank], options={"fuse2": 1}) as one:
+        with lbm.cabi.Simulation(p, devices=[local_rank], options={"fuse2": 1, "persistent": 0}) as one:
             one.upload(full_cells, full_obst)
             for n in PREFLIGHT_SPLIT:
                 one.run(n)

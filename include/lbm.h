@@ -190,6 +190,9 @@ int lbm_debug_pad_nonzero(lbm_ctx *ctx, long long *count);
  * rcp_rn_fast, sqrt_rn_fast) against the correctly rounded __frcp_rn / __fsqrt_rn over all 2^32
  * float bit patterns on the current device; both counts must come back 0. */
 int lbm_debug_fastmath_mismatches(unsigned long long *rcp_bad, unsigned long long *sqrt_bad);
+/* Development aid for the small-deck tile kernel (option "tile_debug" = 1): SM clock stamps of tile 0 over
+ * 64 rounds of the last launch, clocks[64][16] (slot meanings in csrc/lbm_tile.cuh). */
+int lbm_debug_tile_timing(lbm_ctx *ctx, long long *clocks, int rounds, int slots);
 int lbm_device_count(void);
 int lbm_abi_version(void);
 

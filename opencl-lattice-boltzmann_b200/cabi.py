@@ -21,7 +21,7 @@ EXPORTS = [
     "lbm_connect", "lbm_destroy", "lbm_upload", "lbm_halo_push", "lbm_download_cells", "lbm_download_av_vels",
     "lbm_download_av_sums", "lbm_download_final_state", "lbm_combine_av_sums", "lbm_host_alloc", "lbm_host_free", "lbm_run", "lbm_sync",
     "lbm_upload_packed", "lbm_mask_words_per_row", "lbm_pack_obstacles", "lbm_host_alloc_on", "lbm_device_numa_node",
-    "lbm_run_timed", "lbm_set_option", "lbm_get_info", "lbm_debug_pad_nonzero", "lbm_debug_fastmath_mismatches", "lbm_device_count", "lbm_abi_version", "lbm_last_error",
+    "lbm_run_timed", "lbm_set_option", "lbm_get_info", "lbm_debug_pad_nonzero", "lbm_debug_fastmath_mismatches", "lbm_debug_tile_timing", "lbm_device_count", "lbm_abi_version", "lbm_last_error",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library(path: str | None = None):
     lib.lbm_get_info.argtypes = [vp, C.POINTER(LbmInfo)]
     lib.lbm_debug_pad_nonzero.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.lbm_debug_fastmath_mismatches.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.lbm_debug_tile_timing.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.lbm_device_count.argtypes = []
     lib.lbm_abi_version.argtypes = []
     lib.lbm_last_error.argtypes = []
@@ -223,6 +224,12 @@ class Simulation:
         d = {name: getattr(info, name) for name, _ in LbmInfo._fields_}
         d["kernel_name"] = info.kernel_name.decode()
         return d
+
+    def tile_timing(self) -> np.ndarray:
+        """[64, 16] SM clock stamps of tile 0 (option tile_debug = 1); see csrc/lbm_tile.cuh."""
+        out = np.zeros((64, 16), dtype=np.int64)
+        self._ck(self.lib.lbm_debug_tile_timing(self._ctx, C.c_void_p(out.ctypes.data), 64, 16))
+        return out
 
     def pad_nonzero(self) -> int:
         n = C.c_longlong(0)

@@ -114,6 +114,7 @@ struct Slab {
   double2* partials = nullptr;   // chunk_steps x blocks_per_step block partials
   double2* scratch = nullptr;    // chunk_steps x splits range sums of av_finalize_kernel
   unsigned int* tickets = nullptr;
+  long long* tile_timing = nullptr;        // tile_kernel, option tile_debug: phase clocks of tile 0
   unsigned int* progress = nullptr;        // per-block step counters of the persistent kernel
   long long progress_capacity = 0;
   long long pblocks = 0;                   // grid of the persistent kernel
@@ -176,8 +177,8 @@ struct lbm_ctx {
   long long launches = 0;
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
-      opt_tile = -1, opt_tile_steps = 0, opt_tile_w = 0, opt_tile_h = 0,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1;
+      opt_tile_debug = 0, opt_tile = -1, opt_tile_steps = 0, opt_tile_w = 0, opt_tile_h = 0,
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1, opt_f2_st = 0;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256, f2_long = 0;
   int f2_kernel = 2;           // 1: fuse2_tma_kernel (the A/B predecessor), 2: fuse2p_kernel (W = 4 only)
@@ -225,28 +226,33 @@ bool plan_tiles(lbm_ctx* ctx) {
     (void)cudaGetLastError();
     sms = 148;
   }
-  const int want_k = ctx->opt_tile_steps > 0 ? ctx->opt_tile_steps : 4;
-  long long best_cost = -1;
+  // Time model of a round, fitted to the phase clocks of tools/tile_timing.py (profiles/r02_tile_experiments),
+  // in us: a hand-off through L2 (store, fence, flag, poll, halo load) ~2.25, plus per step ~0.30 + 0.0125 per
+  // warp of the haloed tile (the steps are bound by the issue slots of one SM: ~200 instructions per cell).
+  double best = -1.0;
   int best_tx = 0, best_ty = 0, best_k = 0;
-  auto consider = [&](int tx, int ty) {
+  auto consider = [&](int tx, int ty, int want_k) {
     if (tx < 1 || ty < 1 || tx > nx || ty > ny || (long long)tx * ty > sms) return;
     const int w = (nx + tx - 1) / tx, h = (ny + ty - 1) / ty;         // largest tile
     const int k = std::max(1, std::min(want_k, std::min(nx / tx, ny / ty)));   // <= smallest tile's sides
     if ((long long)(w + 2 * k) * (h + 2 * k) > 1024) return;
-    long long cost = 0;
-    for (int i = 1; i <= k; i++) cost += (long long)(w + 2 * (k - i)) * (h + 2 * (k - i));
-    // cost per step (rounds of fewer steps pay the hand-off more often: weigh it like ~600 cell updates)
-    const long long per_step = (cost + 600) * 64 / k;
-    if (best_cost < 0 || per_step < best_cost || (per_step == best_cost && tx < best_tx)) {
-      best_cost = per_step; best_tx = tx; best_ty = ty; best_k = k;
+    const int warps = ((w + 2 * k) * (h + 2 * k) + 31) / 32;
+    double per_step = (2.25 + k * (0.30 + 0.0125 * warps)) / k;
+    if (nx % tx != 0 || ny % ty != 0) per_step *= 1.03;               // ragged tilings: the largest tile sets the pace
+    if (best < 0 || per_step < best - 1e-9 || (per_step < best + 1e-9 && tx < best_tx)) {
+      best = per_step; best_tx = tx; best_ty = ty; best_k = k;
     }
   };
-  if (ctx->opt_tile_w > 0 && ctx->opt_tile_h > 0)
-    consider((nx + ctx->opt_tile_w - 1) / ctx->opt_tile_w, (ny + ctx->opt_tile_h - 1) / ctx->opt_tile_h);
-  else
-    for (int ty = 1; ty <= std::min(ny, sms); ty++)
-      for (int tx = 1; tx <= std::min(nx, sms / ty); tx++) consider(tx, ty);
-  if (best_cost < 0) return false;
+  const int k_lo = ctx->opt_tile_steps > 0 ? ctx->opt_tile_steps : 1;
+  const int k_hi = ctx->opt_tile_steps > 0 ? ctx->opt_tile_steps : 8;
+  for (int k = k_lo; k <= k_hi; k++) {
+    if (ctx->opt_tile_w > 0 && ctx->opt_tile_h > 0)
+      consider((nx + ctx->opt_tile_w - 1) / ctx->opt_tile_w, (ny + ctx->opt_tile_h - 1) / ctx->opt_tile_h, k);
+    else
+      for (int ty = 1; ty <= std::min(ny, sms); ty++)
+        for (int tx = 1; tx <= std::min(nx, sms / ty); tx++) consider(tx, ty, k);
+  }
+  if (best < 0) return false;
   ctx->tiles_x = best_tx;
   ctx->tiles_y = best_ty;
   ctx->tile_K = best_k;
@@ -333,8 +339,8 @@ void resolve_options(lbm_ctx* ctx) {
     const int tx = 128 * ctx->f2_warps;
     // fuse2p_kernel, automatic tiling: every segment start recomputes two warm-up rows (long segments are
     // cheaper), but the launch ends when the LAST block ends (short segments leave a shorter tail), and blocks
-    // are dispatched in index order: so long segments first (2x the uniform length) and short ones (half of
-    // it) for the rows that make up the last ~two rounds of resident blocks (DESIGN.md has the measurement).
+    // are dispatched in index order: so 128-row segments first and 32-row ones for the rows that make up the
+    // last ~two rounds of resident blocks (DESIGN.md has the measurements).
     ctx->f2_long = 0;
     for (auto& s : ctx->slabs) {
       s.f2_strips = (nx + tx - 1) / tx;
@@ -342,11 +348,15 @@ void resolve_options(lbm_ctx* ctx) {
       s.f2_segs_y = (s.rows + ctx->f2_rows - 1) / ctx->f2_rows;
     }
     const bool forced = ctx->opt_f2_long > 0;                       // tests / sweeps: fuse2_long = rows of the long segments
-    // automatic only where it was measured: slabs large enough for the 64-row uniform choice above
-    const bool automatic = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4 && ctx->f2_rows == 64;
+    // automatic only where it was measured: slabs large enough for the 64-row uniform choice above (>= 4096 rows
+    // of 32 strips), and — with a quarter of the slab in short segments — the 32-row one (2048 rows: the per-GPU
+    // slab of the 8-GPU strong-scaling split; 156.0 vs 150.7 GLUPS uniform, tools/f2_rows_sweep.py)
+    const bool auto64 = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4 && ctx->f2_rows == 64;
+    const bool auto32 = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4 && ctx->f2_rows == 32;
+    const bool automatic = auto64 || auto32;
     if (ctx->f2_kernel == 2 && (forced || automatic)) {
-      const int seg_short = forced ? ctx->f2_rows : std::max(8, ctx->f2_rows / 2);
-      const int seg_long = forced ? ctx->opt_f2_long : 2 * ctx->f2_rows;
+      const int seg_short = forced ? ctx->f2_rows : 32;
+      const int seg_long = forced ? ctx->opt_f2_long : 128;
       int sms = 148;
       if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->slabs[0].device) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -354,12 +364,12 @@ void resolve_options(lbm_ctx* ctx) {
       }
       // rows left to the short segments: ~two rounds of resident blocks (3 per SM); forced: a quarter of the slab
       auto rows_short_of = [&](const Slab& s) -> long long {
-        const long long want = forced ? (s.rows + 3) / 4 : (2LL * 3 * sms + s.f2_strips - 1) / s.f2_strips * seg_short;
+        const long long want = (forced || auto32) ? (s.rows + 3) / 4 : (2LL * 3 * sms + s.f2_strips - 1) / s.f2_strips * seg_short;
         return (want + seg_short - 1) / seg_short * seg_short;
       };
       bool ok = true;
       for (auto& s : ctx->slabs)
-        if (seg_long >= s.rows || (!forced && rows_short_of(s) * 2 > s.rows)) ok = false;   // small slab: stay uniform
+        if (forced ? seg_long >= s.rows : (seg_long * 4 > s.rows || rows_short_of(s) * 2 > s.rows)) ok = false;   // small slab: stay uniform
       if (ok) {
         ctx->f2_long = seg_long;
         ctx->f2_rows = seg_short;
@@ -490,7 +500,7 @@ RingPlan plan_of(const lbm_ctx* ctx) {
 
 // A ring wait that timed out left its epoch in the slab's error word (wait_epoch, lbm_kernels.cuh).
 int check_ring_health(lbm_ctx* ctx) {
-  if (ctx->failed) return fail("the ring already failed (a neighbour did not answer); destroy the context");
+  if (ctx->failed) return fail("the context already failed (a wait timed out, see the first error); destroy it");
   if (!ctx->ring) return 0;
   for (auto& s : ctx->slabs) {
     if (set_device(s)) return 1;
@@ -713,7 +723,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
   if (!ctx) return fail("ctx is NULL");
   if (nsteps < 0) return fail("nsteps must be >= 0");
   if (!ctx->uploaded) return fail("lbm_run before lbm_upload");
-  if (ctx->failed) return fail("lbm_run on a failed ring (a neighbour did not answer); destroy the context");
+  if (ctx->failed) return fail("lbm_run on a failed context (a wait timed out earlier); destroy it");
   if (ctx->nranks > 1 && !ctx->connected) return fail("lbm_run before lbm_connect on a %d-rank ring", ctx->nranks);
   if (ms) *ms = 0.f;
   if (nsteps == 0) return 0;
@@ -804,6 +814,12 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
       ta.skip_last_accel = (done + n == nsteps) ? 1 : 0;
       ta.progress = s.progress;
       ta.partials = s.partials;
+      if (ctx->opt_tile_debug && !s.tile_timing) {
+        const size_t bytes = sizeof(long long) * lbm::TILE_TIMING_ROUNDS * lbm::TILE_TIMING_SLOTS;
+        CK(cudaMalloc(&s.tile_timing, bytes));
+        CK(cudaMemsetAsync(s.tile_timing, 0, bytes, s.stream));
+      }
+      ta.timing = ctx->opt_tile_debug ? s.tile_timing : nullptr;
       CK(cudaMemsetAsync(s.progress, 0, sizeof(unsigned int) * 32 * (size_t)ntiles, s.stream));
       void* kargs[] = {&ta};
       CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lbm::tile_kernel), dim3((unsigned)ntiles),
@@ -957,6 +973,7 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         fa.seg_long = ctx->f2_long;
         fa.n_long = s.f2_n_long;
         fa.l2_ahead = ctx->opt_f2_l2ahead;
+        fa.st_hint = ctx->opt_f2_st;
         fa.partials1 = s.partials + (long long)in_chunk * s.pstride;
         fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
         fa.per_step = s.pstride;
@@ -1189,6 +1206,7 @@ void lbm_destroy(lbm_ctx* ctx) {
       if (f) cudaFree(f);
     if (s.partials) { cudaFree(s.partials); cudaFree(s.scratch); cudaFree(s.tickets); }
     if (s.progress) cudaFree(s.progress);
+    if (s.tile_timing) cudaFree(s.tile_timing);
     if (s.av_hi) cudaFree(s.av_hi);
     if (s.av_lo) cudaFree(s.av_lo);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
@@ -1535,6 +1553,7 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "persistent")) ctx->opt_persistent = (int)value;
   else if (!strcmp(key, "chunk_steps")) ctx->opt_chunk = (int)value;
   else if (!strcmp(key, "tile")) ctx->opt_tile = (int)value;
+  else if (!strcmp(key, "tile_debug")) ctx->opt_tile_debug = value ? 1 : 0;   // development: record phase clocks of tile 0
   else if (!strcmp(key, "tile_steps")) ctx->opt_tile_steps = (int)std::max(0L, std::min(64L, value));
   else if (!strcmp(key, "tile_w")) ctx->opt_tile_w = (int)std::max(0L, value);
   else if (!strcmp(key, "tile_h")) ctx->opt_tile_h = (int)std::max(0L, value);
@@ -1548,6 +1567,7 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
     if (value != 1 && value != 2) return fail("fuse2_tma must be 1 (fuse2_tma_kernel) or 2 (fuse2p_kernel)");
     ctx->opt_f2_tma = (int)value;
   }
+  else if (!strcmp(key, "fuse2_st_cs")) ctx->opt_f2_st = value ? 1 : 0;   // experiments: evict-first lattice stores
   else if (!strcmp(key, "fuse2_nlong")) ctx->opt_f2_nlong = (int)value;  // with fuse2_long > 0: how many long segments per strip
   else if (!strcmp(key, "fuse2_long")) ctx->opt_f2_long = (int)value;   // -1 auto, 0 uniform segments, n: rows of the long ones
   else if (!strcmp(key, "fuse2_mode")) ctx->opt_f2_mode = (int)(value & 3);
@@ -1584,6 +1604,22 @@ int lbm_debug_pad_nonzero(lbm_ctx* ctx, long long* count) {
     for (float v : host)
       if (v != 0.0f) (*count)++;
   }
+  return 0;
+}
+
+int lbm_debug_tile_timing(lbm_ctx* ctx, long long* clocks, int rounds, int slots) {
+  // development aid (option "tile_debug" = 1): SM clock stamps of tile 0 / thread 0 of the LAST tile_kernel launch,
+  // rounds 8..71: slot 0 round start, 1 neighbours flags seen, 2 halo in shared memory, 3.. after each step barrier,
+  // 15 own last step done
+  if (!ctx || !clocks) return fail("lbm_debug_tile_timing: NULL argument");
+  if (rounds != lbm::TILE_TIMING_ROUNDS || slots != lbm::TILE_TIMING_SLOTS)
+    return fail("lbm_debug_tile_timing: expected %d x %d", lbm::TILE_TIMING_ROUNDS, lbm::TILE_TIMING_SLOTS);
+  DeviceGuard guard;
+  Slab& s = ctx->slabs[0];
+  if (!s.tile_timing) return fail("lbm_debug_tile_timing: option tile_debug was not set (or no tile_kernel launch yet)");
+  if (set_device(s)) return 1;
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaMemcpy(clocks, s.tile_timing, sizeof(long long) * rounds * slots, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -52,7 +52,10 @@ struct TileArgs {
   int skip_last_accel;       // 1: the launch's last step is the run's last step
   unsigned int* progress;    // [tiles*32] rounds completed by each tile in this launch (one 128-byte line each; zeroed)
   double2* partials;         // [nsteps][tiles] per-tile sum of cell speeds of each step, as (hi, lo)
+  long long* timing;         // optional (development): [TILE_TIMING_ROUNDS][TILE_TIMING_SLOTS] SM clocks of tile 0, thread 0
 };
+
+constexpr int TILE_TIMING_ROUNDS = 64, TILE_TIMING_SLOTS = 16;
 
 // x range [x0, x0+w) of part i of n of an axis of `len` cells (sizes differ by at most one)
 __host__ __device__ inline void tile_range(int len, int n, int i, int& x0, int& w) {
@@ -121,6 +124,11 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
     const int k = min(K, ta.nsteps - s0);              // steps in this round
     const float* src = ta.buf[(ta.first_buf + r) & 1];
     float* dst = ta.buf[(ta.first_buf + r + 1) & 1];
+    // development: phase clocks of tile 0 (slot 0 round start, 1 neighbours' flags seen, 2 halo in shared memory,
+    // 3.. after each step's barrier, 15 own last step done)
+    long long* tm = (ta.timing != nullptr && tile == 0 && tid == 0 && r >= 8 && r < 8 + TILE_TIMING_ROUNDS)
+                        ? ta.timing + (r - 8) * TILE_TIMING_SLOTS : nullptr;
+    if (tm) tm[0] = clock64();
 
     // ---- wait for the neighbours' previous round; meanwhile sum the previous round's speeds ----
     if (r > 0) {
@@ -142,6 +150,7 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
       }
       __syncthreads();
     }
+    if (tm) tm[1] = clock64();
 
     // ---- the haloed tile of the current state -> shared memory (coherent L2 loads: other SMs wrote it) ----
     if (in_tile) {
@@ -150,6 +159,7 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
       for (int q = 0; q < NSPEEDS; q++) A[q * plane + c] = __ldcg(g + q * ta.plane_stride);
     }
     __syncthreads();
+    if (tm) tm[2] = clock64();
 
     // ---- k time steps on chip ----
     float* cur = A;
@@ -185,7 +195,9 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
           for (int q = 0; q < NSPEEDS; q++) nxt[q * plane + c] = o[q];
         }
       }
+      if (tm && i == k) tm[15] = clock64();
       __syncthreads();
+      if (tm && 2 + i < 15) tm[2 + i] = clock64();
       float* sw = cur; cur = nxt; nxt = sw;
     }
 

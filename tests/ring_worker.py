@@ -111,9 +111,9 @@ def main():
         ref_cells, ref_av = oracle_lib.run_f32(p, cells, obstacles, args.steps)
         same = np.array_equal(helpers.bits(full), helpers.bits(ref_cells))
         av_ok = np.allclose(av, ref_av, rtol=2e-6, atol=0)
-        # single-slab run on this GPU (same cells per thread = same segment sums): av_vels must be
-        # bitwise identical to the ring's
-        with lbm.cabi.Simulation(p, devices=[local], options={"cells_per_thread": 4}) as one:
+        # single-slab run on this GPU with the one-step kernel (same cells per thread = same segment sums;
+        # the small-deck tile kernel sums per cell instead): av_vels must be bitwise identical to the ring's
+        with lbm.cabi.Simulation(p, devices=[local], options={"cells_per_thread": 4, "persistent": 0}) as one:
             one.upload(cells, obstacles)
             one.run(args.steps)
             one.sync()

@@ -303,7 +303,7 @@ def test_row_slabs_on_one_gpu_equal_single(lbm, nslabs):
     """The multi-slab path (ghost rows, edge stores into the neighbour, epoch flags) on ONE device:
     lattice and av_vels bitwise equal to the single-slab run."""
     p, cells, obstacles = random_case(256, 41, seed=11, walls=False)
-    a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 9, options={"cells_per_thread": 4})
+    a_cells, a_av, _ = run_gpu(lbm, p, cells, obstacles, 9, options={"cells_per_thread": 4, "persistent": 0})
     b_cells, b_av, info = run_gpu(lbm, p, cells, obstacles, 9, devices=[0] * nslabs, options={"cells_per_thread": 4})
     assert info["nslabs"] == nslabs
     assert np.array_equal(bits(a_cells), bits(b_cells))
