@@ -178,7 +178,7 @@ struct lbm_ctx {
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
       opt_tile_debug = 0, opt_tile = -1, opt_tile_steps = 0, opt_tile_w = 0, opt_tile_h = 0,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1, opt_f2_st = 0;
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256, f2_long = 0;
   int f2_kernel = 2;           // 1: fuse2_tma_kernel (the A/B predecessor), 2: fuse2p_kernel (W = 4 only)
@@ -973,7 +973,6 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         fa.seg_long = ctx->f2_long;
         fa.n_long = s.f2_n_long;
         fa.l2_ahead = ctx->opt_f2_l2ahead;
-        fa.st_hint = ctx->opt_f2_st;
         fa.partials1 = s.partials + (long long)in_chunk * s.pstride;
         fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
         fa.per_step = s.pstride;
@@ -1567,7 +1566,6 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
     if (value != 1 && value != 2) return fail("fuse2_tma must be 1 (fuse2_tma_kernel) or 2 (fuse2p_kernel)");
     ctx->opt_f2_tma = (int)value;
   }
-  else if (!strcmp(key, "fuse2_st_cs")) ctx->opt_f2_st = value ? 1 : 0;   // experiments: evict-first lattice stores
   else if (!strcmp(key, "fuse2_nlong")) ctx->opt_f2_nlong = (int)value;  // with fuse2_long > 0: how many long segments per strip
   else if (!strcmp(key, "fuse2_long")) ctx->opt_f2_long = (int)value;   // -1 auto, 0 uniform segments, n: rows of the long ones
   else if (!strcmp(key, "fuse2_mode")) ctx->opt_f2_mode = (int)(value & 3);

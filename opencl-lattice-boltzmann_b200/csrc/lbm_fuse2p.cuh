@@ -367,14 +367,8 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
       float tot = cells(g, l1, l5, l8, r3, r6, r7, bits, accel, out);
       if (active) {
         float* d = a.dst + (long long)y * a.pitch + xb;
-        if (fa.st_hint) {
 #pragma unroll
-          for (int k = 0; k < NSPEEDS; k++)
-            __stcs(reinterpret_cast<float4*>(d + k * ps), make_float4(out[k][0], out[k][1], out[k][2], out[k][3]));
-        } else {
-#pragma unroll
-          for (int k = 0; k < NSPEEDS; k++) store_vec<V, 0>(d + k * ps, out[k]);
-        }
+        for (int k = 0; k < NSPEEDS; k++) store_vec<V, 0>(d + k * ps, out[k]);
         if (y >= rows - 2) {   // the up neighbour's ghost rows -1, -2
           float* gh = a.up_ghost + (long long)(y - (rows - 1)) * a.pitch + xb;
 #pragma unroll

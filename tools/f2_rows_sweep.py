@@ -36,6 +36,9 @@ for nx, ny in shapes:
     out = []
     for t in tilings:
         opts = {"fuse2": 1, "persistent": 0}
+        for kv in filter(None, os.environ.get("F2_OPTS", "").split(",")):   # e.g. F2_OPTS=fuse2_st_cs=1
+            key, val = kv.split("=")
+            opts[key] = int(val)
         if t != "auto":
             if "/" in t:     # long/short[/number of long segments per strip]
                 parts = [int(v) for v in t.split("/")]
