@@ -12,6 +12,14 @@ the whole grid.  `value` = cells * K / device time (CUDA events on the launching
 ranks) with the lattice resident in HBM; `e2e` = the reference's own timed region
 (d2q9-bgk.c:196-263: upload + K steps + sync + download) through the C-ABI with pinned HOST buffers.
 
+Beside it, in the same JSON line:
+  N = 1   `decks`: the four reference decks (configs[0..3]) at full maxIters through the same C-ABI — us/step,
+          MLUPS, the reference's timed region, av_vels against the golden — with the CPU oracle's time for the
+          same deck; `cpu_baseline`; `roofline.no_arithmetic_ceiling`.
+  N > 1   `parity_check`: BEFORE anything is timed, a 16384 x 512*N ring case run for 3 + 4 steps and compared
+          bitwise with the CPU oracle on the whole grid (exit code 3 and nothing timed on a mismatch);
+          `strong`: the N = 1 grid (16384 x 16384) split N ways, with the same grid timed on rank 0's GPU alone.
+
 --impl reference times the reference's algorithm on the box's host cores: the OpenMP fp32 CPU
 restatement in oracle/ (the reference's OpenCL host cannot be built in this image), each step one
 time step of a bounded 16384-wide sample of the same deck.
