@@ -227,8 +227,8 @@ bool plan_tiles(lbm_ctx* ctx) {
     sms = 148;
   }
   // Time model of a round, fitted to the phase clocks of tools/tile_timing.py (profiles/r02_tile_experiments),
-  // in us: a hand-off through L2 (store, fence, flag, poll, halo load) ~2.25, plus per step ~0.30 + 0.0125 per
-  // warp of the haloed tile (the steps are bound by the issue slots of one SM: ~200 instructions per cell).
+  // in us: a hand-off through L2 (store, fence, flag, poll, halo load) ~2.0, plus per step ~0.30 + 0.010 per
+  // warp of the haloed tile, or 0.022 per warp once the SM's issue slots are the bound (~160 instructions per cell).
   double best = -1.0;
   int best_tx = 0, best_ty = 0, best_k = 0;
   auto consider = [&](int tx, int ty, int want_k) {
@@ -237,7 +237,7 @@ bool plan_tiles(lbm_ctx* ctx) {
     const int k = std::max(1, std::min(want_k, std::min(nx / tx, ny / ty)));   // <= smallest tile's sides
     if ((long long)(w + 2 * k) * (h + 2 * k) > 1024) return;
     const int warps = ((w + 2 * k) * (h + 2 * k) + 31) / 32;
-    double per_step = (2.25 + k * (0.30 + 0.0125 * warps)) / k;
+    double per_step = (2.0 + k * std::max(0.30 + 0.010 * warps, 0.022 * warps)) / k;
     if (nx % tx != 0 || ny % ty != 0) per_step *= 1.03;               // ragged tilings: the largest tile sets the pace
     if (best < 0 || per_step < best - 1e-9 || (per_step < best + 1e-9 && tx < best_tx)) {
       best = per_step; best_tx = tx; best_ty = ty; best_k = k;

@@ -64,9 +64,15 @@ __host__ __device__ inline void tile_range(int len, int n, int i, int& x0, int& 
   x0 = i * base + (i < rem ? i : rem);
 }
 
+// A block has at most 1024 threads = haloed cells, so every shared-memory plane gets the same fixed stride:
+// plane offsets are then immediates of the LDS / STS instructions instead of per-step address arithmetic
+// (the steps are bound by issue slots, ~1 instruction per cycle and scheduler: every instruction counts).
+constexpr int TILE_PLANE = 1024;
+
 __host__ __device__ inline int tile_smem_bytes(int lw, int lh, int K, int max_owned) {
-  // two copies of nine haloed planes + K steps of owned-cell speeds
-  return (2 * NSPEEDS * lw * lh + K * max_owned) * (int)sizeof(float);
+  // two copies of nine planes + K steps of owned-cell speeds
+  (void)lw; (void)lh;
+  return (2 * NSPEEDS * TILE_PLANE + K * max_owned) * (int)sizeof(float);
 }
 
 __device__ __forceinline__ int wrap(int v, int n) {   // v in [-n, 2n)
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
   tile_range(ny, ta.tiles_y, tyi, y0, h);
   const int LW = ta.lw;                       // smem row stride (the largest tile's haloed width)
   const int lwt = w + 2 * K, lht = h + 2 * K; // this tile's haloed size
-  const int plane = LW * ta.lh;
+  constexpr int plane = TILE_PLANE;
   float* A = tsm;
   float* B = tsm + NSPEEDS * plane;
   float* speeds = tsm + 2 * NSPEEDS * plane;  // [K][max_owned]; this tile uses [K][w*h]
@@ -161,45 +167,57 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
     __syncthreads();
     if (tm) tm[2] = clock64();
 
-    // ---- k time steps on chip ----
+    // ---- k time steps on chip: k-1 steps from one shared-memory copy to the other, the last one to the lattice ----
+    // (two separate code paths: the global addresses of the last step stay out of the shared-memory steps, whose
+    // issue slots are what bounds the round)
+    auto pull_collide = [&](const float* cur, int i, float (&o)[NSPEEDS]) -> float {
+      float t[NSPEEDS];
+      const float* pc = cur + c;                     // own row; the row below / above at -LW / +LW
+      const float* ps = pc - LW;
+      const float* pn = pc + LW;
+      t[0] = pc[0 * plane];                          // pull, kernels.cl:104-112
+      t[1] = pc[1 * plane - 1];
+      t[2] = ps[2 * plane];
+      t[3] = pc[3 * plane + 1];
+      t[4] = pn[4 * plane];
+      t[5] = ps[5 * plane - 1];
+      t[6] = ps[6 * plane + 1];
+      t[7] = pn[7 * plane + 1];
+      t[8] = pn[8 * plane - 1];
+      const float sp = collide_cell(t, fluid, ta.omega, o);
+      if (accel_cell && !(ta.skip_last_accel && s0 + i == ta.nsteps)) accelerate_cell(o, fluid, ta.w1, ta.w2);
+      return sp;
+    };
     float* cur = A;
     float* nxt = B;
-    for (int i = 1; i <= k; i++) {
-      const bool last_of_round = (i == k);
-      const bool active = last_of_round ? owned : (margin >= i);
-      if (active) {
-        float t[NSPEEDS], o[NSPEEDS];
-        t[0] = cur[0 * plane + c];                     // pull, kernels.cl:104-112
-        t[1] = cur[1 * plane + c - 1];
-        t[2] = cur[2 * plane + c - LW];
-        t[3] = cur[3 * plane + c + 1];
-        t[4] = cur[4 * plane + c + LW];
-        t[5] = cur[5 * plane + c - LW - 1];
-        t[6] = cur[6 * plane + c - LW + 1];
-        t[7] = cur[7 * plane + c + LW + 1];
-        t[8] = cur[8 * plane + c + LW - 1];
-        const float sp = collide_cell(t, fluid, ta.omega, o);
-        const bool fold = accel_cell && !(ta.skip_last_accel && s0 + i == ta.nsteps);
-        if (fold) accelerate_cell(o, fluid, ta.w1, ta.w2);
-        if (owned) speeds[(i - 1) * nown + own_idx] = sp;
-        if (last_of_round) {
-          float* g = dst + goff;
+    float* spd = speeds + own_idx;                   // this cell's slot of step i-1 (owned cells only)
+    for (int i = 1; i < k; i++) {
+      if (margin >= i) {
+        float o[NSPEEDS];
+        const float sp = pull_collide(cur, i, o);
+        if (owned) *spd = sp;
 #pragma unroll
-          for (int q = 0; q < NSPEEDS; q++) g[q * ta.plane_stride] = o[q];
-          if (r == rounds - 1 && ghost_off != 0) {
-#pragma unroll
-            for (int q = 0; q < NSPEEDS; q++) g[q * ta.plane_stride + ghost_off] = o[q];
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < NSPEEDS; q++) nxt[q * plane + c] = o[q];
-        }
+        for (int q = 0; q < NSPEEDS; q++) nxt[c + q * plane] = o[q];
       }
-      if (tm && i == k) tm[15] = clock64();
+      spd += nown;
       __syncthreads();
       if (tm && 2 + i < 15) tm[2 + i] = clock64();
       float* sw = cur; cur = nxt; nxt = sw;
     }
+    if (owned) {
+      float o[NSPEEDS];
+      *spd = pull_collide(cur, k, o);
+      float* g = dst + goff;
+#pragma unroll
+      for (int q = 0; q < NSPEEDS; q++) g[q * ta.plane_stride] = o[q];
+      if (r == rounds - 1 && ghost_off != 0) {
+#pragma unroll
+        for (int q = 0; q < NSPEEDS; q++) g[q * ta.plane_stride + ghost_off] = o[q];
+      }
+    }
+    if (tm) tm[15] = clock64();
+    __syncthreads();
+    if (tm && 2 + k < 15) tm[2 + k] = clock64();
 
     // ---- publish: this tile's state after round r is in the other lattice ----
     if (tid == 0) {
