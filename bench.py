@@ -628,7 +628,7 @@ def decks_block(lbm, cpu=True):
     for name in DECKS:
         p, cells, obstacles = lbm.decks.load_deck(*lbm.decks.deck_paths(name))
         n = p.maxIters
-        out = np.empty_like(cells)
+        cells_out = np.empty_like(cells)
         with lbm.cabi.Simulation(p, devices=[0]) as sim:
             sim.upload(cells, obstacles)
             sim.run(min(2000, n))      # warm-up (module load, clocks)
@@ -643,7 +643,7 @@ def decks_block(lbm, cpu=True):
                 sim.upload(cells, obstacles)
                 sim.run(n)
                 sim.sync()
-                sim.download_cells(out)
+                sim.download_cells(cells_out)
                 sim.download_av_vels(n)
                 dt = time.perf_counter() - t0
                 region = dt if region is None else min(region, dt)
