@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
       t[6] = ps[6 * plane + 1];
       t[7] = pn[7 * plane + 1];
       t[8] = pn[8 * plane - 1];
-      const float sp = collide_cell(t, fluid, ta.omega, o);
+      const float sp = collide_cell(t, fluid, ta.omega, o, owned);   // only the tile's own cells are summed
       if (accel_cell && !(ta.skip_last_accel && s0 + i == ta.nsteps)) accelerate_cell(o, fluid, ta.w1, ta.w2);
       return sp;
     };
