@@ -178,7 +178,7 @@ struct lbm_ctx {
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
       opt_tile_debug = 0, opt_tile = -1, opt_tile_steps = 0, opt_tile_w = 0, opt_tile_h = 0,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1, opt_f2_cluster = 0, opt_f2_order = 0;
+      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256, f2_long = 0;
   int f2_kernel = 2;           // 1: fuse2_tma_kernel (the A/B predecessor), 2: fuse2p_kernel (W = 4 only)
@@ -683,7 +683,7 @@ int launch_fuse2_tma(int warps, int packed, const lbm::Fuse2Args& fa, long long 
 }
 
 template <int W, bool PACKED, bool FULLW, int MODE>
-int launch_fuse2p_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st, int cluster) {
+int launch_fuse2p_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
   static bool configured[64] = {};
   int dev = 0;
   CK(cudaGetDevice(&dev));
@@ -694,24 +694,6 @@ int launch_fuse2p_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st, i
                             cudaSharedmemCarveoutMaxShared));
     configured[dev] = true;
   }
-  if (cluster > 1 && grid % cluster == 0) {
-    // experiment (option fuse2_cluster): the blocks of `cluster` adjacent strips as one thread-block cluster — no
-    // cluster feature is used, only the co-scheduling: adjacent strips start together and stay on the same rows
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(32 * (W + 1));
-    cfg.dynamicSmemBytes = lbm::fuse2p_smem_bytes<W>();
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, lbm::fuse2p_kernel<W, PACKED, FULLW, MODE>, fa));
-    return 0;
-  }
   lbm::fuse2p_kernel<W, PACKED, FULLW, MODE><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2p_smem_bytes<W>(), st>>>(fa);
   return 0;
 }
@@ -719,12 +701,12 @@ int launch_fuse2p_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st, i
 // the re-pipelined two-step kernel (lbm_fuse2p.cuh): 512-column strips.  mode bit 0: one reciprocal /
 // square-root range check per thread instead of per pair (packed only); bit 1: dry run (bandwidth
 // experiments only)
-int launch_fuse2p(int packed, bool fullw, int mode, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st, int cluster) {
+int launch_fuse2p(int packed, bool fullw, int mode, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
 #define F2P_(P, F)                                                                  \
   do {                                                                              \
-    if (mode & 2) return launch_fuse2p_t<4, P, F, 2>(fa, grid, st, cluster);        \
-    if (P && (mode & 1)) return launch_fuse2p_t<4, P, F, 1>(fa, grid, st, cluster); \
-    return launch_fuse2p_t<4, P, F, 0>(fa, grid, st, cluster);                      \
+    if (mode & 2) return launch_fuse2p_t<4, P, F, 2>(fa, grid, st);                 \
+    if (P && (mode & 1)) return launch_fuse2p_t<4, P, F, 1>(fa, grid, st);          \
+    return launch_fuse2p_t<4, P, F, 0>(fa, grid, st);                               \
   } while (0)
   if (packed) { if (fullw) F2P_(true, true); else F2P_(true, false); }
   if (fullw) F2P_(false, true); else F2P_(false, false);
@@ -991,13 +973,12 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         fa.seg_long = ctx->f2_long;
         fa.n_long = s.f2_n_long;
         fa.l2_ahead = ctx->opt_f2_l2ahead;
-        fa.order = ctx->ring ? 0 : ctx->opt_f2_order;
         fa.partials1 = s.partials + (long long)in_chunk * s.pstride;
         fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
         fa.per_step = s.pstride;
         const long long f2grid = (long long)s.f2_strips * s.f2_segs_y;
         const int rc = ctx->f2_kernel == 2
-                           ? launch_fuse2p(ctx->packed, ctx->p.nx % 512 == 0, ctx->opt_f2_mode, fa, f2grid, s.stream, ctx->opt_f2_cluster)
+                           ? launch_fuse2p(ctx->packed, ctx->p.nx % 512 == 0, ctx->opt_f2_mode, fa, f2grid, s.stream)
                            : launch_fuse2_tma(ctx->f2_warps, ctx->packed, fa, f2grid, s.stream);
         if (rc) return 1;
       } else {
@@ -1585,8 +1566,6 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
     if (value != 1 && value != 2) return fail("fuse2_tma must be 1 (fuse2_tma_kernel) or 2 (fuse2p_kernel)");
     ctx->opt_f2_tma = (int)value;
   }
-  else if (!strcmp(key, "fuse2_order")) ctx->opt_f2_order = value ? 1 : 0;   // experiments
-  else if (!strcmp(key, "fuse2_cluster")) ctx->opt_f2_cluster = (int)std::max(0L, std::min(8L, value));   // experiments
   else if (!strcmp(key, "fuse2_nlong")) ctx->opt_f2_nlong = (int)value;  // with fuse2_long > 0: how many long segments per strip
   else if (!strcmp(key, "fuse2_long")) ctx->opt_f2_long = (int)value;   // -1 auto, 0 uniform segments, n: rows of the long ones
   else if (!strcmp(key, "fuse2_mode")) ctx->opt_f2_mode = (int)(value & 3);

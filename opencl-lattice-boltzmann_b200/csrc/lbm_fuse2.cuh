@@ -37,7 +37,6 @@ struct Fuse2Args {
   int seg_rows;            // rows per segment
   int seg_long, n_long;    // fuse2p_kernel: the first n_long segments of a strip have seg_long rows (0: all seg_rows)
   int l2_ahead;            // TMA kernel: rows ahead of the stage load that are prefetched into L2 (0 = off; measured: off is best)
-  int order;               // fuse2p_kernel, experiments (single slab only): 1 = consecutive blocks walk the segments of one strip
   double2* partials1;      // Σ|u| partials of the first step  [per_step entries, first strips*segs_y used]
   double2* partials2;      // Σ|u| partials of the second step
   long long per_step;      // entries per step in the partial buffer (the tail is zeroed here)

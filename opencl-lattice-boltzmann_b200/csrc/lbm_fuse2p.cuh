@@ -91,8 +91,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 3) fuse2p_kernel(const __grid_co
   int strip, sy;
   {
     const int b = blockIdx.x, ns = fa.strips;
-    if (fa.order == 1) { strip = b / fa.segs_y; sy = b - strip * fa.segs_y; }
-    else if (fa.segs_y < 2 || b < ns) { sy = b / ns; strip = b - sy * ns; }
+    if (fa.segs_y < 2 || b < ns) { sy = b / ns; strip = b - sy * ns; }
     else if (b < 2 * ns) { sy = fa.segs_y - 1; strip = b - ns; }
     else { sy = 1 + (b - 2 * ns) / ns; strip = (b - 2 * ns) % ns; }
   }
