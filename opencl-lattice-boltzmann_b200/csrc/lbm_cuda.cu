@@ -322,14 +322,31 @@ void resolve_options(lbm_ctx* ctx) {
   // the grid (strips x segments) should fill the ~444 resident blocks of a B200 a few times over
   {
     const long long strips = (nx + 128 * ctx->f2_warps - 1) / (128 * ctx->f2_warps);
-    // measured best (tools/f2_rows_sweep.py): about 2048 blocks, between 16 and 64 rows per segment
+    // large slabs, measured best (tools/f2_rows_sweep.py): about 2048 blocks, 32 or 64 rows per segment (refined
+    // into long + short segments below)
     int seg = 64;
     while (seg > 16 && min_rows * strips / seg < 2048) seg >>= 1;
+    if (seg == 16) {
+      // mid-size slabs (fewer than ~64 Ki row-strips): the grid is only a few waves of the 3 x SMs resident
+      // blocks, so what matters is that the LAST wave is full: the segment length with the least
+      // waves x (rows + warm-up) (tools/sizes_bench.py: 2048^2 with 16-row segments = 512 blocks = 1.15 waves)
+      int sms = 148;
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->slabs[0].device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        sms = 148;
+      }
+      const long long slots = 3LL * sms;
+      long long best_cost = -1;
+      for (int cand = 8; cand <= 96 && cand <= min_rows; cand++) {
+        const long long blocks = strips * ((min_rows + cand - 1) / cand);
+        const long long cost = (blocks + slots - 1) / slots * (cand + 3);
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; seg = cand; }   // ties: the longer segment
+      }
+    }
     ctx->f2_rows = ctx->opt_f2_rows >= 4 ? ctx->opt_f2_rows : seg;
-    const long long blocks = strips * ((min_rows + ctx->f2_rows - 1) / ctx->f2_rows);
-    // auto: on when the lattice is streamed from HBM and the grid fills the GPU at least once
-    // (measured 128.4 vs 95 GLUPS at 16384^2); smaller lattices keep the one-step kernel
-    ctx->fuse2 = can_fuse && (ctx->opt_fuse2 >= 0 ? ctx->opt_fuse2 != 0 : blocks >= 444);
+    // auto: on when the lattice is streamed from HBM and the grid can fill most of the GPU
+    // (measured 128.4 vs 95 GLUPS at 16384^2; 104.7 vs 74.7 at 1536^2); smaller lattices keep the one-step kernel
+    ctx->fuse2 = can_fuse && (ctx->opt_fuse2 >= 0 ? ctx->opt_fuse2 != 0 : min_rows * strips >= 4096);
   }
   if (ctx->fuse2) {
     // the two-step kernel is issue-bound, not HBM-bound: the packed fp32x2 arithmetic pays there

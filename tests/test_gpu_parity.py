@@ -232,6 +232,20 @@ def test_two_step_kernel_two_segment_sizes(lbm, oracle, nx, ny, long_rows, short
     assert np.array_equal(bits(got_av), bits(one_av))
 
 
+@pytest.mark.parametrize("nx,ny", [(1536, 1536), (1792, 1200), (2048, 1100)])
+def test_two_step_kernel_mid_size_automatic_tiling(lbm, oracle, nx, ny):
+    """Mid-size lattices (streamed from HBM, but only a few waves of blocks): the automatic choice is the two-step
+    kernel with the segment length that fills the last wave (odd lengths such as 11 or 19 rows, ragged last
+    segments and, for nx = 1792, a ragged last strip) — bits equal the oracle's."""
+    p, cells, obstacles = lbm.decks.synthetic_channel(nx, ny, block=16, spacing=128)
+    cells = lbm.decks.perturbed_rows(cells, 0)
+    ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 5, reference_order=False)
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 5)
+    assert info["kernel_name"].startswith("fuse2p_kernel<"), info
+    assert np.array_equal(bits(got_cells), bits(ref_cells)), info
+    np.testing.assert_allclose(got_av, ref_av, rtol=1e-5, atol=0)   # (the oracle adds its row sums in fp32)
+
+
 def test_fast_reciprocal_and_square_root_exhaustive(lbm):
     """rcp_rn_fast / sqrt_rn_fast (MUFU + packed Newton step, one shared range check) return the bits of
     __frcp_rn / __fsqrt_rn for every one of the 2^32 float bit patterns inside their range."""

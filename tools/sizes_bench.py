@@ -24,7 +24,11 @@ def main():
         a, ka = run(n, {}, steps)
         b, kb = run(n, {"fuse2": 0, "persistent": 0}, steps)
         c, kc = run(n, {"fuse2": 1, "persistent": 0}, steps)
-        print(f"{n:6d}^2 steps {steps:5d}: auto {a:9.0f} MLUPS [{ka}] | one-step {b:9.0f} | two-step {c:9.0f} [{kc}]", flush=True)
+        line = f"{n:6d}^2 steps {steps:5d}: auto {a:9.0f} MLUPS [{ka}] | one-step {b:9.0f} | two-step {c:9.0f} [{kc}]"
+        if 2.0 * 36.0 * n * n <= 200e6:      # small enough to try the persistent kernel too
+            d, kd = run(n, {"persistent": 1}, steps)
+            line += f" | persistent {d:9.0f}"
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
