@@ -228,7 +228,7 @@ PREFLIGHT_ROWS = 512      # rows per rank of the N-rank parity pre-flight
 PREFLIGHT_SPLIT = (3, 4)  # two lbm_run calls: an odd tail (one-step kernel) + a split run
 
 
-def preflight_parity(lbm, torch, dist, rank, world, local_rank, barrier):
+def preflight_parity(lbm, torch, dist, rank, world, local_rank, barrier, emit):
     """N > 1 only, before anything is timed: a seeded 16384 x (512 N) ring case, 7 steps run as 3 + 4
     (odd tail + split run) with the two-step kernel and the long/short segment tiling of the bench
     workload, compared on rank 0 BITWISE with the CPU oracle on the whole grid (per-slab checksums of
@@ -308,8 +308,8 @@ def preflight_parity(lbm, torch, dist, rank, world, local_rank, barrier):
     dist.broadcast(ok, 0)
     if int(ok.item()) != 1:
         if rank == 0:
-            print(json.dumps({"metric": "MLUPS", "value": None, "n_gpus": world, "parity_check": result,
-                              "error": "multi-GPU parity pre-flight FAILED: nothing was timed"}), flush=True)
+            emit({"metric": "MLUPS", "value": None, "n_gpus": world, "parity_check": result,
+                  "error": "multi-GPU parity pre-flight FAILED: nothing was timed"})
         dist.barrier()
         dist.destroy_process_group()
         raise SystemExit(3)
@@ -333,10 +333,20 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # stdout must carry exactly ONE line (the JSON): libraries that print there (NCCL's version banner at communicator
+    # creation, whatever NCCL_DEBUG says) are sent to stderr until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL would print its version banner on stdout, before the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -360,7 +370,7 @@ def run_b200_arm(args):
 
     parity = None
     if world > 1 and not args.no_parity_check:
-        parity = preflight_parity(lbm, torch, dist, rank, world, local_rank, barrier)
+        parity = preflight_parity(lbm, torch, dist, rank, world, local_rank, barrier, emit)
 
     nx, rows = NX, args.rows_per_gpu
     if args.scaling == "strong":       # total work fixed: the 16384-row grid split into N slabs
@@ -606,7 +616,7 @@ def run_b200_arm(args):
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     for buf in (pin_cells, pin_obst, pin_out):
         buf.close()
     if world > 1:

@@ -64,21 +64,25 @@ __host__ __device__ inline void tile_range(int len, int n, int i, int& x0, int& 
   x0 = i * base + (i < rem ? i : rem);
 }
 
-// A block has at most 1024 threads = haloed cells, so every shared-memory plane gets the same fixed stride:
+// A block has at most 1024 threads = haloed cells (times the cells per thread), so every shared-memory plane gets the
+// same fixed stride:
 // plane offsets are then immediates of the LDS / STS instructions instead of per-step address arithmetic
 // (the steps are bound by issue slots, ~1 instruction per cycle and scheduler: every instruction counts).
 constexpr int TILE_PLANE = 1024;
 
-__host__ __device__ inline int tile_smem_bytes(int lw, int lh, int K, int max_owned) {
+__host__ __device__ inline int tile_smem_bytes(int cells_per_thread, int K, int max_owned) {
   // two copies of nine planes + K steps of owned-cell speeds
-  (void)lw; (void)lh;
-  return (2 * NSPEEDS * TILE_PLANE + K * max_owned) * (int)sizeof(float);
+  return (2 * NSPEEDS * TILE_PLANE * cells_per_thread + K * max_owned) * (int)sizeof(float);
 }
 
 __device__ __forceinline__ int wrap(int v, int n) {   // v in [-n, 2n)
   return v < 0 ? v + n : (v >= n ? v - n : v);
 }
 
+// CPT = cells per thread (1 or 2): a block of at most 1024 threads steps a haloed tile of up to CPT * 1024 cells.
+// CPT = 1 is the kernel of the reference's three small decks; CPT = 2 extends it to lattices of up to ~260 K cells
+// (512 x 512), which would otherwise fall to the persistent kernel's one-hand-off-per-step (tools/sizes_bench.py).
+template <int CPT>
 __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ TileArgs ta) {
   extern __shared__ __align__(16) float tsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -91,30 +95,37 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
   tile_range(ny, ta.tiles_y, tyi, y0, h);
   const int LW = ta.lw;                       // smem row stride (the largest tile's haloed width)
   const int lwt = w + 2 * K, lht = h + 2 * K; // this tile's haloed size
-  constexpr int plane = TILE_PLANE;
+  constexpr int plane = TILE_PLANE * CPT;
   float* A = tsm;
   float* B = tsm + NSPEEDS * plane;
   float* speeds = tsm + 2 * NSPEEDS * plane;  // [K][max_owned]; this tile uses [K][w*h]
   const int nown = w * h;
 
-  // ---- per-thread constants: the cell of the haloed tile this thread owns for the whole launch ----
-  const int lx = tid % LW, ly = tid / LW;
-  const bool in_tile = lx < lwt && ly < lht;
-  const int margin = in_tile ? min(min(lx, lwt - 1 - lx), min(ly, lht - 1 - ly)) : -1;   // cells from the halo's rim
-  const int gx = wrap((x0 - K + lx) % nx, nx), gy = wrap((y0 - K + ly) % ny, ny);
-  const bool owned = margin >= K;
-  const int own_idx = (ly - K) * w + (lx - K);
-  const int c = ly * LW + lx;                 // index in a smem plane
-  bool fluid = true, accel_cell = false;
-  long long goff = 0;
-  if (in_tile) {
-    fluid = ((ta.mask[(long long)gy * ta.mask_pitch + (gx >> 5)] >> (gx & 31)) & 1u) == 0u;
-    accel_cell = (gy == ta.accel_row);
-    goff = (long long)gy * ta.pitch + gx;
+  // ---- per-thread constants: the cells of the haloed tile this thread owns for the whole launch ----
+  int c[CPT], margin[CPT], own_idx[CPT];       // index in a smem plane; cells from the halo's rim (-1: no cell)
+  bool fluid[CPT], accel_cell[CPT], owned[CPT];
+  long long goff[CPT], ghost_off[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; j++) {
+    c[j] = tid + j * (int)blockDim.x;
+    const int lx = c[j] % LW, ly = c[j] / LW;
+    const bool in_tile = lx < lwt && ly < lht;
+    margin[j] = in_tile ? min(min(lx, lwt - 1 - lx), min(ly, lht - 1 - ly)) : -1;
+    const int gx = wrap((x0 - K + lx) % nx, nx), gy = wrap((y0 - K + ly) % ny, ny);
+    owned[j] = margin[j] >= K;
+    own_idx[j] = (ly - K) * w + (lx - K);
+    fluid[j] = true;
+    accel_cell[j] = false;
+    goff[j] = 0;
+    if (in_tile) {
+      fluid[j] = ((ta.mask[(long long)gy * ta.mask_pitch + (gx >> 5)] >> (gx & 31)) & 1u) == 0u;
+      accel_cell[j] = (gy == ta.accel_row);
+      goff[j] = (long long)gy * ta.pitch + gx;
+    }
+    // ghost rows of the arena mirror the lattice's edge rows (other kernels read them): kept up to date by the
+    // launch's last round.  Row y < 2 is also ghost row ny + y; row y >= ny-2 is also ghost row y - ny.
+    ghost_off[j] = (gy < 2) ? (long long)ny * ta.pitch : (gy >= ny - 2) ? -(long long)ny * ta.pitch : 0;
   }
-  // ghost rows of the arena mirror the lattice's edge rows (other kernels read them): kept up to date by the
-  // launch's last round.  Row y < 2 is also ghost row ny + y; row y >= ny-2 is also ghost row y - ny.
-  const long long ghost_off = (gy < 2) ? (long long)ny * ta.pitch : (gy >= ny - 2) ? -(long long)ny * ta.pitch : 0;
 
   // the eight neighbouring tiles (periodic); thread j < 8 polls neighbour j
   int nb_tile = tile;
@@ -159,20 +170,22 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
     if (tm) tm[1] = clock64();
 
     // ---- the haloed tile of the current state -> shared memory (coherent L2 loads: other SMs wrote it) ----
-    if (in_tile) {
-      const float* g = src + goff;
 #pragma unroll
-      for (int q = 0; q < NSPEEDS; q++) A[q * plane + c] = __ldcg(g + q * ta.plane_stride);
-    }
+    for (int j = 0; j < CPT; j++)
+      if (margin[j] >= 0) {
+        const float* g = src + goff[j];
+#pragma unroll
+        for (int q = 0; q < NSPEEDS; q++) A[q * plane + c[j]] = __ldcg(g + q * ta.plane_stride);
+      }
     __syncthreads();
     if (tm) tm[2] = clock64();
 
     // ---- k time steps on chip: k-1 steps from one shared-memory copy to the other, the last one to the lattice ----
     // (two separate code paths: the global addresses of the last step stay out of the shared-memory steps, whose
     // issue slots are what bounds the round)
-    auto pull_collide = [&](const float* cur, int i, float (&o)[NSPEEDS]) -> float {
+    auto pull_collide = [&](const float* cur, int i, int cc, bool fl, bool ac, bool own, float (&o)[NSPEEDS]) -> float {
       float t[NSPEEDS];
-      const float* pc = cur + c;                     // own row; the row below / above at -LW / +LW
+      const float* pc = cur + cc;                    // own row; the row below / above at -LW / +LW
       const float* ps = pc - LW;
       const float* pn = pc + LW;
       t[0] = pc[0 * plane];                          // pull, kernels.cl:104-112
@@ -184,37 +197,41 @@ __global__ void __launch_bounds__(1024, 1) tile_kernel(const __grid_constant__ T
       t[6] = ps[6 * plane + 1];
       t[7] = pn[7 * plane + 1];
       t[8] = pn[8 * plane - 1];
-      const float sp = collide_cell(t, fluid, ta.omega, o, owned);   // only the tile's own cells are summed
-      if (accel_cell && !(ta.skip_last_accel && s0 + i == ta.nsteps)) accelerate_cell(o, fluid, ta.w1, ta.w2);
+      const float sp = collide_cell(t, fl, ta.omega, o, own);   // only the tile's own cells are summed
+      if (ac && !(ta.skip_last_accel && s0 + i == ta.nsteps)) accelerate_cell(o, fl, ta.w1, ta.w2);
       return sp;
     };
     float* cur = A;
     float* nxt = B;
-    float* spd = speeds + own_idx;                   // this cell's slot of step i-1 (owned cells only)
+    float* spd = speeds;                             // the slots of step i-1
     for (int i = 1; i < k; i++) {
-      if (margin >= i) {
-        float o[NSPEEDS];
-        const float sp = pull_collide(cur, i, o);
-        if (owned) *spd = sp;
 #pragma unroll
-        for (int q = 0; q < NSPEEDS; q++) nxt[c + q * plane] = o[q];
-      }
+      for (int j = 0; j < CPT; j++)
+        if (margin[j] >= i) {
+          float o[NSPEEDS];
+          const float sp = pull_collide(cur, i, c[j], fluid[j], accel_cell[j], owned[j], o);
+          if (owned[j]) spd[own_idx[j]] = sp;
+#pragma unroll
+          for (int q = 0; q < NSPEEDS; q++) nxt[c[j] + q * plane] = o[q];
+        }
       spd += nown;
       __syncthreads();
       if (tm && 2 + i < 15) tm[2 + i] = clock64();
       float* sw = cur; cur = nxt; nxt = sw;
     }
-    if (owned) {
-      float o[NSPEEDS];
-      *spd = pull_collide(cur, k, o);
-      float* g = dst + goff;
 #pragma unroll
-      for (int q = 0; q < NSPEEDS; q++) g[q * ta.plane_stride] = o[q];
-      if (r == rounds - 1 && ghost_off != 0) {
+    for (int j = 0; j < CPT; j++)
+      if (owned[j]) {
+        float o[NSPEEDS];
+        spd[own_idx[j]] = pull_collide(cur, k, c[j], fluid[j], accel_cell[j], true, o);
+        float* g = dst + goff[j];
 #pragma unroll
-        for (int q = 0; q < NSPEEDS; q++) g[q * ta.plane_stride + ghost_off] = o[q];
+        for (int q = 0; q < NSPEEDS; q++) g[q * ta.plane_stride] = o[q];
+        if (r == rounds - 1 && ghost_off[j] != 0) {
+#pragma unroll
+          for (int q = 0; q < NSPEEDS; q++) g[q * ta.plane_stride + ghost_off[j]] = o[q];
+        }
       }
-    }
     if (tm) tm[15] = clock64();
     __syncthreads();
     if (tm && 2 + k < 15) tm[2 + k] = clock64();

@@ -66,7 +66,7 @@ def test_persistent_kernel_bit_exact(lbm, oracle, V, tpb):
 
 
 TILE_SHAPES = [(128, 128), (128, 256), (256, 256), (100, 37), (34, 9), (33, 5), (8, 4), (1, 4), (300, 200), (4096, 8),
-               (5, 700)]
+               (5, 700), (384, 384), (512, 512), (500, 301)]      # the last three: two cells per thread
 
 
 @pytest.mark.parametrize("nx,ny", TILE_SHAPES)
@@ -76,8 +76,9 @@ def test_tile_kernel_bit_exact(lbm, oracle, nx, ny):
     and long thin grids; 11 steps = rounds of 4 + 4 + 3."""
     p, cells, obstacles = random_case(nx, ny, seed=nx * 31 + ny, walls=False)
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 11)
-    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 11)
+    got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 11, options={"tile": 1})   # (forced: also one-step rounds)
     assert info["kernel_name"].startswith("tile_kernel<"), info
+    assert ("2/thread" in info["kernel_name"]) == (nx * ny > 120000), info
     assert np.array_equal(bits(got_cells), bits(ref_cells)), info
     np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
 
