@@ -15,13 +15,13 @@ import oracle_lib  # noqa: E402
 
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 200
-    persistent = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-    shapes = [(256, 64), (128, 128), (384, 24), (512, 96), (1024, 64)]
+    persistent = int(sys.argv[2]) if len(sys.argv) > 2 else 1      # -1: the automatic choice (tile kernel on these shapes)
+    shapes = [(256, 64), (128, 128), (384, 24), (512, 96), (1024, 64), (384, 384), (200, 333)]
     refs = {}
     bad = 0
     for it in range(iters):
         nx, ny = shapes[it % len(shapes)]
-        nsteps = 7 + (it % 3)
+        nsteps = 7 + (it % 3) + (40 if persistent < 0 else 0)       # several rounds of the tile kernel
         key = (nx, ny, nsteps)
         p, cells, obstacles = helpers.random_case(nx, ny, seed=nx * 1000 + ny)
         if key not in refs:
