@@ -26,7 +26,7 @@ DECK=128x128
 
 all: $(LIB) $(EXE) $(EXE).exe oracle
 
-$(LIB): $(PKG)/csrc/lbm_cuda.cu $(PKG)/csrc/lbm_kernels.cuh $(PKG)/csrc/lbm_fuse2.cuh $(PKG)/csrc/lbm_fuse2p.cuh $(PKG)/csrc/lbm_tile.cuh include/lbm.h
+$(LIB): $(PKG)/csrc/lbm_cuda.cu $(PKG)/csrc/lbm_kernels.cuh $(PKG)/csrc/lbm_fuse2.cuh $(PKG)/csrc/lbm_fuse2p.cuh $(PKG)/csrc/lbm_fuse2q.cuh $(PKG)/csrc/lbm_tile.cuh include/lbm.h
 	$(NVCC) $(NVCCFLAGS) -shared -Iinclude $< -o $@
 
 $(EXE): $(PKG)/host/d2q9_bgk_main.c $(PKG)/host/lbm_io.c $(PKG)/host/lbm_io.h include/lbm.h $(LIB)

@@ -499,7 +499,7 @@ def run_b200_arm(args):
 
     # ---- the kernel's own memory ceiling: the same launches without the arithmetic (it wrecks the lattice) ----
     dry = None
-    if world == 1 and info1["kernel_name"].startswith("fuse2p_kernel") and not args.no_dry_run:
+    if world == 1 and info1["kernel_name"].startswith("fuse2") and not args.no_dry_run:
         try:
             sim.set_option("fuse2_mode", 3)     # bit 1: same bulk copies, ring traffic, barriers and stores, no collision
             sim.run(4)
@@ -508,7 +508,7 @@ def run_b200_arm(args):
             ms_dry = sim.run_timed(nd)
             dry = {"mlups": round(cells_total * nd / (ms_dry * 1e-3) / 1e6, 1), "steps": nd,
                    "frac_of_ceiling": round(mlups / (cells_total * nd / (ms_dry * 1e-3) / 1e6), 4),
-                   "note": "fuse2p_kernel with option fuse2_mode bit 1: identical memory traffic and synchronisation, "
+                   "note": "the two-step kernel with option fuse2_mode bit 1: identical memory traffic and synchronisation, "
                            "arithmetic removed (results are garbage, measured after everything else); "
                            "value / this = how much of the arithmetic the kernel hides behind HBM"}
         except Exception as e:

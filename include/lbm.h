@@ -176,8 +176,8 @@ int lbm_run_timed(lbm_ctx *ctx, int nsteps, float *ms);
  * caching, 1: .cs hints), "persistent" (-1 auto, 0, 1), "global_barrier", "chunk_steps",
  * "tile" (-1 auto, 0, 1: the multi-step tile kernel for lattices that fit the SMs' shared memory),
  * "tile_steps" (time steps per hand-off), "tile_w", "tile_h" (tile size), "fuse2" (-1 auto, 0, 1: two
- * time steps per launch), "fuse2_tma" (which two-step kernel: 1 first TMA-staged version, 2 re-pipelined =
- * default), "fuse2_rows", "fuse2_long" (-1 auto, 0 uniform row segments, n: rows of the leading long
+ * time steps per launch), "fuse2_tma" (which two-step kernel: 3 fuse2q_kernel, two-deep stage = default; 2 fuse2p_kernel,
+ * its one-deep predecessor, also used for scalar arithmetic and fuse2_mode 0), "fuse2_rows", "fuse2_long" (-1 auto, 0 uniform row segments, n: rows of the leading long
  * segments), "fuse2_mode" (bit 0: one reciprocal/sqrt range check per thread; bit 1: dry run without
  * arithmetic for bandwidth experiments — garbage results), "wait_timeout_ms" (ring waits; any time).
  * Unknown key -> non-zero. */

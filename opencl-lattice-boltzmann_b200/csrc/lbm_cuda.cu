@@ -10,6 +10,7 @@
 #include "lbm_kernels.cuh"
 #include "lbm_fuse2.cuh"
 #include "lbm_fuse2p.cuh"
+#include "lbm_fuse2q.cuh"
 #include "lbm_tile.cuh"
 
 #include <cuda_runtime.h>
@@ -178,10 +179,10 @@ struct lbm_ctx {
   // options
   int opt_v = 0, opt_tpb = 0, opt_streaming = -1, opt_persistent = -1, opt_chunk = 0, opt_sync = 0, opt_tps = 0, opt_packed = -1,
       opt_tile_debug = 0, opt_tile = -1, opt_tile_steps = 0, opt_tile_w = 0, opt_tile_h = 0,
-      opt_fuse2 = -1, opt_f2_warps = 0, opt_f2_rows = 0, opt_f2_tma = 2, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1;
+      opt_fuse2 = -1, opt_f2_rows = 0, opt_f2_tma = 3, opt_f2_l2ahead = 0, opt_f2_mode = 1, opt_f2_long = -1, opt_f2_nlong = -1;
   // resolved
   int fuse2 = 0, f2_warps = 4, f2_rows = 256, f2_long = 0;
-  int f2_kernel = 2;           // 1: fuse2_tma_kernel (the A/B predecessor), 2: fuse2p_kernel (W = 4 only)
+  int f2_kernel = 3;           // 3: fuse2q_kernel (two-deep stage, packed arithmetic), 2: fuse2p_kernel (its A/B predecessor)
   int V = 1, tpb = 256, tps = 1024, packed = 0, streaming = 0, chunk_steps = 1, segs = 1, persistent = 0;
   // the multi-step tile kernel (lbm_tile.cuh): tiling of the lattice, steps per hand-off, block size
   int tile_cpt = 1;            // cells per thread of the tile kernel (1: up to 1024 haloed cells per tile, 2: up to 2048)
@@ -319,8 +320,8 @@ void resolve_options(lbm_ctx* ctx) {
 
   // two time steps per HBM pass (lbm_fuse2.cuh): 128-bit kernel only, lattices streamed from HBM,
   // every slab of the ring at least 4 rows (an even split, so every rank decides alike)
-  ctx->f2_warps = (ctx->opt_f2_warps == 2 || ctx->opt_f2_warps == 4 || ctx->opt_f2_warps == 8) ? ctx->opt_f2_warps : 4;
-  ctx->f2_kernel = (ctx->opt_f2_tma == 2 && ctx->f2_warps != 4) ? 1 : ctx->opt_f2_tma;   // fuse2p_kernel: 512-column strips only
+  ctx->f2_warps = 4;                                  // 512-column strips
+  ctx->f2_kernel = ctx->opt_f2_tma == 2 ? 2 : 3;      // refined below: the two-deep-stage kernel exists for packed arithmetic only
   const long long total_slabs = (long long)ctx->nranks * (long long)ctx->slabs.size();
   // the smallest slab of the even split (the same number on every rank of a ring, so all decide alike)
   // and this context's own smallest slab (lbm_create_slab takes any row range; lbm_connect rejects a
@@ -361,6 +362,7 @@ void resolve_options(lbm_ctx* ctx) {
   if (ctx->fuse2) {
     // the two-step kernel is issue-bound, not HBM-bound: the packed fp32x2 arithmetic pays there
     if (ctx->opt_packed < 0) ctx->packed = 1;
+    if (!ctx->packed || (ctx->opt_f2_mode & 3) == 0) ctx->f2_kernel = 2;   // (nor for the per-pair range check, fuse2_mode 0)
     if (ctx->packed && ctx->opt_tps != 1024) ctx->tps = 768;   // odd tail step: packed needs ~80 registers
     ctx->chunk_steps = std::max(2, ctx->chunk_steps);
     const int tx = 128 * ctx->f2_warps;
@@ -381,7 +383,7 @@ void resolve_options(lbm_ctx* ctx) {
     const bool auto64 = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4 && ctx->f2_rows == 64;
     const bool auto32 = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4 && ctx->f2_rows == 32;
     const bool automatic = auto64 || auto32;
-    if (ctx->f2_kernel == 2 && (forced || automatic)) {
+    if (ctx->f2_kernel >= 2 && (forced || automatic)) {
       const int seg_short = forced ? ctx->f2_rows : 32;
       const int seg_long = forced ? ctx->opt_f2_long : 128;
       int sms = 148;
@@ -689,26 +691,6 @@ int launch_persistent(const Variant& v, const lbm::PersistArgs& pa, long long gr
 #undef CALL_
 }
 
-template <int W, bool PACKED, int MINB>
-int launch_fuse2_tma_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
-  static bool configured[64] = {};
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
-  if (dev < 64 && !configured[dev]) {
-    CK(cudaFuncSetAttribute(lbm::fuse2_tma_kernel<W, PACKED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            lbm::fuse2_tma_smem_bytes<W>()));
-    configured[dev] = true;
-  }
-  lbm::fuse2_tma_kernel<W, PACKED, MINB><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2_tma_smem_bytes<W>(), st>>>(fa);
-  return 0;
-}
-
-int launch_fuse2_tma(int warps, int packed, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
-  if (warps == 2) return packed ? launch_fuse2_tma_t<2, true, 5>(fa, grid, st) : launch_fuse2_tma_t<2, false, 5>(fa, grid, st);
-  if (warps == 8) return packed ? launch_fuse2_tma_t<8, true, 1>(fa, grid, st) : launch_fuse2_tma_t<8, false, 1>(fa, grid, st);
-  return packed ? launch_fuse2_tma_t<4, true, 3>(fa, grid, st) : launch_fuse2_tma_t<4, false, 3>(fa, grid, st);
-}
-
 template <int W, bool PACKED, bool FULLW, int MODE>
 int launch_fuse2p_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
   static bool configured[64] = {};
@@ -738,6 +720,28 @@ int launch_fuse2p(int packed, bool fullw, int mode, const lbm::Fuse2Args& fa, lo
   if (packed) { if (fullw) F2P_(true, true); else F2P_(true, false); }
   if (fullw) F2P_(false, true); else F2P_(false, false);
 #undef F2P_
+}
+
+template <int W, bool PACKED, bool FULLW, int MODE>
+int launch_fuse2q_t(const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  static bool configured[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    CK(cudaFuncSetAttribute(lbm::fuse2q_kernel<W, PACKED, FULLW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            lbm::fuse2q_smem_bytes<W>()));
+    CK(cudaFuncSetAttribute(lbm::fuse2q_kernel<W, PACKED, FULLW, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    configured[dev] = true;
+  }
+  lbm::fuse2q_kernel<W, PACKED, FULLW, MODE><<<(unsigned)grid, 32 * (W + 1), lbm::fuse2q_smem_bytes<W>(), st>>>(fa);
+  return 0;
+}
+
+// the two-deep-stage variant of the re-pipelined two-step kernel (lbm_fuse2q.cuh); packed arithmetic only
+int launch_fuse2q(bool fullw, int mode, const lbm::Fuse2Args& fa, long long grid, cudaStream_t st) {
+  if (fullw) return (mode & 2) ? launch_fuse2q_t<4, true, true, 2>(fa, grid, st) : launch_fuse2q_t<4, true, true, 1>(fa, grid, st);
+  return (mode & 2) ? launch_fuse2q_t<4, true, false, 2>(fa, grid, st) : launch_fuse2q_t<4, true, false, 1>(fa, grid, st);
 }
 
 // local row of global row ny-2 in this slab, or -1
@@ -1010,9 +1014,9 @@ int run_impl(lbm_ctx* ctx, int nsteps, bool timed, float* ms) {
         fa.partials2 = s.partials + (long long)(in_chunk + 1) * s.pstride;
         fa.per_step = s.pstride;
         const long long f2grid = (long long)s.f2_strips * s.f2_segs_y;
-        const int rc = ctx->f2_kernel == 2
-                           ? launch_fuse2p(ctx->packed, ctx->p.nx % 512 == 0, ctx->opt_f2_mode, fa, f2grid, s.stream)
-                           : launch_fuse2_tma(ctx->f2_warps, ctx->packed, fa, f2grid, s.stream);
+        const int rc = ctx->f2_kernel == 3
+                           ? launch_fuse2q(ctx->p.nx % 512 == 0, ctx->opt_f2_mode, fa, f2grid, s.stream)
+                           : launch_fuse2p(ctx->packed, ctx->p.nx % 512 == 0, ctx->opt_f2_mode, fa, f2grid, s.stream);
         if (rc) return 1;
       } else {
         if (s.pstride > s.blocks)   // (tiny grids only) the step kernel writes s.blocks partials: clear the rest
@@ -1593,10 +1597,9 @@ int lbm_set_option(lbm_ctx* ctx, const char* key, long value) {
   else if (!strcmp(key, "threads_per_sm")) ctx->opt_tps = (int)value;
   else if (!strcmp(key, "packed")) ctx->opt_packed = (int)value;
   else if (!strcmp(key, "fuse2")) ctx->opt_fuse2 = (int)value;
-  else if (!strcmp(key, "fuse2_warps")) ctx->opt_f2_warps = (int)value;
   else if (!strcmp(key, "fuse2_rows")) ctx->opt_f2_rows = (int)value;
   else if (!strcmp(key, "fuse2_tma")) {
-    if (value != 1 && value != 2) return fail("fuse2_tma must be 1 (fuse2_tma_kernel) or 2 (fuse2p_kernel)");
+    if (value != 2 && value != 3) return fail("fuse2_tma must be 2 (fuse2p_kernel) or 3 (fuse2q_kernel, the default)");
     ctx->opt_f2_tma = (int)value;
   }
   else if (!strcmp(key, "fuse2_nlong")) ctx->opt_f2_nlong = (int)value;  // with fuse2_long > 0: how many long segments per strip
@@ -1700,7 +1703,7 @@ int lbm_get_info(lbm_ctx* ctx, lbm_info* info) {
     if (ctx->f2_long > 0) snprintf(rows, sizeof rows, "%d/%d", ctx->f2_long, ctx->f2_rows);   // long / short segments
     else snprintf(rows, sizeof rows, "%d", ctx->f2_rows);
     snprintf(info->kernel_name, sizeof info->kernel_name, "%s<W=%d,packed=%d,rows=%s>",
-             ctx->f2_kernel == 2 ? "fuse2p_kernel" : "fuse2_tma_kernel", ctx->f2_warps,
+             ctx->f2_kernel == 3 ? "fuse2q_kernel" : "fuse2p_kernel", ctx->f2_warps,
              ctx->packed, rows);
   }
   else

@@ -50,7 +50,7 @@ def run(lbm, deck, **kw):
 def test_full_size_matches_oracle_and_kernels_agree(lbm, oracle, deck):
     p, cells, obstacles = deck
     two, av_two, info_two = run(lbm, deck)                                   # default: two-step kernel
-    assert info_two["kernel_name"].startswith("fuse2p_kernel") and "rows=128/32" in info_two["kernel_name"]
+    assert info_two["kernel_name"].startswith("fuse2q_kernel") and "rows=128/32" in info_two["kernel_name"]
     cs_two = checksum(two)
     # the oracle on the whole 16384 x 16384 grid, all host cores (oracle/lbm_oracle.c, OpenMP over rows)
     lib = oracle.load("fastest")
@@ -80,6 +80,6 @@ def test_full_size_matches_oracle_and_kernels_agree(lbm, oracle, deck):
     del one
 
     ring, av_ring, info_ring = run(lbm, deck, devices=[0, 0])                  # two row slabs, two-step kernel
-    assert info_ring["nslabs"] == 2 and info_ring["kernel_name"].startswith("fuse2p_kernel")
+    assert info_ring["nslabs"] == 2 and info_ring["kernel_name"].startswith("fuse2q_kernel")
     assert checksum(ring) == cs_two
     assert np.array_equal(av_ring.view(np.uint32), av_two.view(np.uint32))

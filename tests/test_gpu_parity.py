@@ -163,12 +163,12 @@ def test_packed_and_register_bound_variants_bit_exact(lbm, oracle, tps, packed, 
 FUSE2_SHAPES = [(256, 64), (1024, 16), (100, 37), (4096, 8), (520, 40), (8, 4), (16384, 12)]
 
 
-F2_NAMES = {1: "fuse2_tma_kernel", 2: "fuse2p_kernel"}
+F2_NAMES = {2: "fuse2p_kernel", 3: "fuse2q_kernel"}
 
 
 @pytest.mark.parametrize("nx,ny", FUSE2_SHAPES)
 @pytest.mark.parametrize("nsteps", [8, 7])
-@pytest.mark.parametrize("tma", [2, 1])
+@pytest.mark.parametrize("tma", [3, 2])
 def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps, tma):
     """Temporal blocking (two time steps per HBM pass, step-1 rows in a shared-memory ring) gives the
     same bits as the oracle; 7 steps = three fused pairs + one single step."""
@@ -181,19 +181,18 @@ def test_two_step_kernel_bit_exact(lbm, oracle, nx, ny, nsteps, tma):
     np.testing.assert_allclose(got_av, ref_av, rtol=AV_RTOL, atol=0)
 
 
-@pytest.mark.parametrize("warps", [2, 4, 8])
 @pytest.mark.parametrize("packed", [0, 1])
 @pytest.mark.parametrize("seg_rows", [4, 10, 256])
-@pytest.mark.parametrize("tma", [2, 1])
-def test_two_step_kernel_variants(lbm, oracle, warps, packed, seg_rows, tma):
-    """Strip width, row-segment length (redundant warm-up rows at every segment start) and packed
-    arithmetic do not change a bit; av_vels equal the one-step kernel's bitwise."""
+@pytest.mark.parametrize("tma", [3, 2])
+def test_two_step_kernel_variants(lbm, oracle, packed, seg_rows, tma):
+    """Row-segment length (redundant warm-up rows at every segment start), packed arithmetic and the stage depth
+    (fuse2q_kernel: two-deep stage + a second barrier per row; fuse2p_kernel: its predecessor) do not change a
+    bit; av_vels equal the one-step kernel's bitwise.  (Scalar arithmetic always runs fuse2p_kernel.)"""
     p, cells, obstacles = random_case(1280, 37, seed=77, walls=False)
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 6)
-    opts = {"persistent": 0, "fuse2": 1, "fuse2_warps": warps, "fuse2_rows": seg_rows, "packed": packed,
-            "fuse2_tma": tma}
+    opts = {"persistent": 0, "fuse2": 1, "fuse2_rows": seg_rows, "packed": packed, "fuse2_tma": tma}
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 6, options=opts)
-    assert f"W={warps}" in info["kernel_name"]
+    assert info["kernel_name"].startswith((F2_NAMES[tma] if packed else "fuse2p_kernel") + "<W=4"), info
     assert np.array_equal(bits(got_cells), bits(ref_cells))
     one_cells, one_av, _ = run_gpu(lbm, p, cells, obstacles, 6, options={"persistent": 0, "fuse2": 0, "cells_per_thread": 4})
     assert np.array_equal(bits(got_av), bits(one_av))
@@ -202,32 +201,36 @@ def test_two_step_kernel_variants(lbm, oracle, warps, packed, seg_rows, tma):
 @pytest.mark.parametrize("nx,ny", [(1024, 40), (1280, 37), (100, 37), (8, 4)])
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("packed", [0, 1])
-def test_repipelined_two_step_kernel(lbm, oracle, nx, ny, mode, packed):
+@pytest.mark.parametrize("tma", [3, 2])
+def test_repipelined_two_step_kernel(lbm, oracle, nx, ny, mode, packed, tma):
     """fuse2p_kernel (body warps arrive on an `empty` mbarrier once the stage is in registers, the halo
     warp requests the next row's bulk copies; obstacle words and the periodic wrap columns travel with the
     copies; packed reciprocal / square root with one range check per pair or per thread): full-width and
-    ragged strips, including the outermost strips' wrap; bits equal the oracle's, av_vels the one-step kernel's."""
+    ragged strips, including the outermost strips' wrap; bits equal the oracle's, av_vels the one-step kernel's.
+    fuse2q_kernel (two-deep stage) exists for packed arithmetic with the per-thread range check; the other
+    combinations run fuse2p_kernel whatever fuse2_tma says."""
     p, cells, obstacles = random_case(nx, ny, seed=nx * 7 + ny, walls=False)
     ref_cells, _ = oracle.run_f32(p, cells, obstacles, 9)
-    opts = {"persistent": 0, "fuse2": 1, "fuse2_tma": 2, "fuse2_rows": 8, "fuse2_mode": mode, "packed": packed}
+    opts = {"persistent": 0, "fuse2": 1, "fuse2_tma": tma, "fuse2_rows": 8, "fuse2_mode": mode, "packed": packed}
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 9, options=opts)
-    assert info["kernel_name"].startswith("fuse2p_kernel<")
+    assert info["kernel_name"].startswith((F2_NAMES[tma] if packed and mode else "fuse2p_kernel") + "<")
     assert np.array_equal(bits(got_cells), bits(ref_cells))
     _, one_av, _ = run_gpu(lbm, p, cells, obstacles, 9, options={"persistent": 0, "fuse2": 0, "cells_per_thread": 4})
     assert np.array_equal(bits(got_av), bits(one_av))
 
 
+@pytest.mark.parametrize("tma", [3, 2])
 @pytest.mark.parametrize("nx,ny,long_rows,short_rows,nslabs", [(1024, 40, 12, 4, 1), (1280, 37, 10, 8, 1), (512, 41, 6, 4, 2),
                                                                 (1024, 64, 16, 4, 3)])
-def test_two_step_kernel_two_segment_sizes(lbm, oracle, nx, ny, long_rows, short_rows, nslabs):
+def test_two_step_kernel_two_segment_sizes(lbm, oracle, nx, ny, long_rows, short_rows, nslabs, tma):
     """Long row segments first, short ones for the last quarter of a slab (the automatic tiling of large slabs,
     forced here on small ones): same bits as the oracle and as the one-step kernel, also on a ring of slabs
     whose edge segments have different lengths."""
     p, cells, obstacles = random_case(nx, ny, seed=nx + 3 * ny, walls=False)
     ref_cells, _ = oracle.run_f32(p, cells, obstacles, 7)
-    opts = {"persistent": 0, "fuse2": 1, "fuse2_tma": 2, "fuse2_rows": short_rows, "fuse2_long": long_rows}
+    opts = {"persistent": 0, "fuse2": 1, "fuse2_tma": tma, "fuse2_rows": short_rows, "fuse2_long": long_rows}
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 7, devices=[0] * nslabs, options=opts)
-    assert info["kernel_name"].startswith("fuse2p_kernel<") and f"rows={long_rows}/{short_rows}>" in info["kernel_name"]
+    assert info["kernel_name"].startswith(F2_NAMES[tma] + "<") and f"rows={long_rows}/{short_rows}>" in info["kernel_name"]
     assert np.array_equal(bits(got_cells), bits(ref_cells))
     _, one_av, _ = run_gpu(lbm, p, cells, obstacles, 7, options={"persistent": 0, "fuse2": 0, "cells_per_thread": 4})
     assert np.array_equal(bits(got_av), bits(one_av))
@@ -242,7 +245,7 @@ def test_two_step_kernel_mid_size_automatic_tiling(lbm, oracle, nx, ny):
     cells = lbm.decks.perturbed_rows(cells, 0)
     ref_cells, ref_av = oracle.run_f32(p, cells, obstacles, 5, reference_order=False)
     got_cells, got_av, info = run_gpu(lbm, p, cells, obstacles, 5)
-    assert info["kernel_name"].startswith("fuse2p_kernel<"), info
+    assert info["kernel_name"].startswith("fuse2q_kernel<"), info
     assert np.array_equal(bits(got_cells), bits(ref_cells)), info
     np.testing.assert_allclose(got_av, ref_av, rtol=1e-5, atol=0)   # (the oracle adds its row sums in fp32)
 
@@ -254,7 +257,7 @@ def test_fast_reciprocal_and_square_root_exhaustive(lbm):
     assert (rcp_bad, sqrt_bad) == (0, 0)
 
 
-@pytest.mark.parametrize("tma", [2, 1])
+@pytest.mark.parametrize("tma", [3, 2])
 def test_two_step_kernel_cells_at_rest(lbm, oracle, tma):
     """Exactly symmetric dyadic populations: u_sq is exactly 0 in the first step (and wherever the
     symmetry survives), which is outside the fast square root's range — the built-in fall-back

@@ -28,7 +28,7 @@ def test_ring_matches_oracle(world, ny, fuse2):
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "lattice_bit_exact=True" in proc.stdout and "av_bitwise_vs_1gpu=True" in proc.stdout
-    assert ("fuse2p_kernel" in proc.stdout) == bool(fuse2)
+    assert ("fuse2q_kernel" in proc.stdout) == bool(fuse2)
 
 
 def test_absent_neighbour_times_out_loudly():
@@ -79,7 +79,7 @@ def test_single_process_multi_device_ring(ngpus, fuse2):
         sim.run(7)
         sim.sync()
         got, av, info = sim.download_cells(), sim.download_av_vels(13), sim.info()
-    assert info["nslabs"] == ngpus and ("fuse2p_kernel" in info["kernel_name"]) == bool(fuse2)
+    assert info["nslabs"] == ngpus and ("fuse2q_kernel" in info["kernel_name"]) == bool(fuse2)
     assert np.array_equal(helpers.bits(got), helpers.bits(ref_cells))
     with lbm.cabi.Simulation(p, devices=[0], options={"cells_per_thread": 4, "persistent": 0}) as one:
         one.upload(cells, obstacles)

@@ -105,7 +105,7 @@ def main():
     name = kname
     if m:
         name = f"step_kernel<V={m.group(1)},hint={m.group(2)},tpb={m.group(3)},tps={m.group(4)},packed={m.group(5)}>"
-    m = re.search(r"(fuse2p_kernel|fuse2_tma_kernel|fuse2_kernel)<(\d+), (\d+)", kname)
+    m = re.search(r"(fuse2q_kernel|fuse2p_kernel|fuse2_tma_kernel|fuse2_kernel)<(\d+), (\d+)", kname)
     if m:
         steps = 2
         rows = sys.argv[4] if len(sys.argv) > 4 else "128"
