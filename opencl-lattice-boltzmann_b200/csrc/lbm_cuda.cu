@@ -378,14 +378,16 @@ void resolve_options(lbm_ctx* ctx) {
     }
     const bool forced = ctx->opt_f2_long > 0;                       // tests / sweeps: fuse2_long = rows of the long segments
     // automatic only where it was measured: slabs large enough for the 64-row uniform choice above (>= 4096 rows
-    // of 32 strips), and — with a quarter of the slab in short segments — the 32-row one (2048 rows: the per-GPU
-    // slab of the 8-GPU strong-scaling split; 156.0 vs 150.7 GLUPS uniform, tools/f2_rows_sweep.py)
+    // of 32 strips: 128-row segments, then 32-row ones), and the class below it (64 Ki .. 128 Ki row-strips, e.g.
+    // the 2048-row slab of the 8-GPU strong-scaling split): 64-row segments, then 16-row ones.  fuse2q_kernel,
+    // tools/f2_rows_sweep.py: 16384x2048 164.3 GLUPS (128/32 with a quarter short: 157.4; uniform 32: 161.0),
+    // 16384x3072 169.6 (157.9; 164.2), 8192x4096 163.6 (156.5; 160.2), 4096x8192 161.8 (155.0; 159.0)
     const bool auto64 = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4 && ctx->f2_rows == 64;
     const bool auto32 = ctx->opt_f2_long < 0 && ctx->opt_f2_rows < 4 && ctx->f2_rows == 32;
     const bool automatic = auto64 || auto32;
     if (ctx->f2_kernel >= 2 && (forced || automatic)) {
-      const int seg_short = forced ? ctx->f2_rows : 32;
-      const int seg_long = forced ? ctx->opt_f2_long : 128;
+      const int seg_short = forced ? ctx->f2_rows : auto32 ? 16 : 32;
+      const int seg_long = forced ? ctx->opt_f2_long : auto32 ? 64 : 128;
       int sms = 148;
       if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->slabs[0].device) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -393,7 +395,7 @@ void resolve_options(lbm_ctx* ctx) {
       }
       // rows left to the short segments: ~two rounds of resident blocks (3 per SM); forced: a quarter of the slab
       auto rows_short_of = [&](const Slab& s) -> long long {
-        const long long want = (forced || auto32) ? (s.rows + 3) / 4 : (2LL * 3 * sms + s.f2_strips - 1) / s.f2_strips * seg_short;
+        const long long want = forced ? (s.rows + 3) / 4 : (2LL * 3 * sms + s.f2_strips - 1) / s.f2_strips * seg_short;
         return (want + seg_short - 1) / seg_short * seg_short;
       };
       bool ok = true;

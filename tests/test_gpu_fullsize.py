@@ -83,3 +83,12 @@ def test_full_size_matches_oracle_and_kernels_agree(lbm, oracle, deck):
     assert info_ring["nslabs"] == 2 and info_ring["kernel_name"].startswith("fuse2q_kernel")
     assert checksum(ring) == cs_two
     assert np.array_equal(av_ring.view(np.uint32), av_two.view(np.uint32))
+    del ring
+
+    # eight row slabs of 2048 rows: the per-GPU slab of the 8-GPU strong-scaling split and its own automatic
+    # tiling (64-row segments, then 16-row ones)
+    ring8, av_ring8, info_ring8 = run(lbm, deck, devices=[0] * 8)
+    assert info_ring8["nslabs"] == 8 and info_ring8["kernel_name"].startswith("fuse2q_kernel")
+    assert "rows=64/16" in info_ring8["kernel_name"], info_ring8
+    assert checksum(ring8) == cs_two
+    assert np.array_equal(av_ring8.view(np.uint32), av_two.view(np.uint32))

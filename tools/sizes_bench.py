@@ -7,7 +7,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opencl_lattice_boltzmann_b200 as lbm  # noqa: E402
 
 
+EXTRA = {k: int(v) for k, v in (kv.split("=") for kv in filter(None, os.environ.get("LBM_OPTS", "").split(",")))}
+
+
 def run(n, opts, steps):
+    opts = {**EXTRA, **opts}      # e.g. LBM_OPTS=fuse2_tma=2 for the A/B predecessor of the two-step kernel
     p, cells, obstacles = lbm.decks.synthetic_channel(n, n)
     with lbm.cabi.Simulation(p, options=opts) as sim:
         sim.upload(cells, obstacles)
