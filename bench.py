@@ -18,7 +18,8 @@ Beside it, in the same JSON line:
           same deck; `cpu_baseline`; `roofline.no_arithmetic_ceiling`.
   N > 1   `parity_check`: BEFORE anything is timed, a 16384 x 512*N ring case run for 3 + 4 steps and compared
           bitwise with the CPU oracle on the whole grid (exit code 3 and nothing timed on a mismatch);
-          `strong`: the N = 1 grid (16384 x 16384) split N ways, with the same grid timed on rank 0's GPU alone.
+          `strong`: the N = 1 grid (16384 x 16384) split N ways, with the same grid timed on rank 0's GPU alone
+          and every av_vels value of the two runs compared bitwise (exit code 3 on a mismatch).
 
 --impl reference times the reference's algorithm on the box's host cores: the OpenMP fp32 CPU
 restatement in oracle/ (the reference's OpenCL host cannot be built in this image), each step one
@@ -524,13 +525,14 @@ def run_b200_arm(args):
         sim_s = make_sim(q, rank * rows_s, rows_s)
         obst_s = np.ascontiguousarray(lbm.decks.synthetic_channel_rows(nx, ny_s, rank * rows_s, rows_s))
         upload(sim_s, c=np.ascontiguousarray(cells_h[:, :rows_s, :]), o=obst_s)   # (the initial state is uniform)
-        sim_s.run(max(2, args.warmup) & ~1)
+        warm_s = max(2, args.warmup) & ~1
+        sim_s.run(warm_s)
         sim_s.sync()
         barrier()
         ms_s = max_over_ranks(sim_s.run_timed(args.steps))
         barrier()
         info_s = sim_s.info()
-        hi_s, lo_s = sim_s.download_av_sums(args.steps)
+        sums_s = gather(sim_s.download_av_sums(warm_s + args.steps))
         sim_s.close()
         strong_mlups = nx * ny_s * args.steps / (ms_s * 1e-3) / 1e6
         # the same grid on ONE GPU (rank 0), for the efficiency: the other ranks wait
@@ -540,17 +542,33 @@ def run_b200_arm(args):
                 o1 = np.ascontiguousarray(lbm.decks.synthetic_channel_rows(nx, ny_s, 0, ny_s))
                 c1 = cells_h if rows == ny_s else np.ascontiguousarray(np.broadcast_to(cells_h[:, :1, :], (9, ny_s, nx)))
                 one.upload(c1, o1)
-                one.run(max(2, args.warmup) & ~1)
+                one.run(warm_s)
                 one.sync()
                 n1 = nx * ny_s * args.steps / (one.run_timed(args.steps) * 1e-3) / 1e6
+                # every av_vels value of the split run (warm-up + timed steps: each one a sum over the whole lattice)
+                # must equal the single-GPU run's bit for bit: the sums are exact, so any halo error would show
+                av_split = lbm.cabi.combine_av_sums(np.stack([x[0] for x in sums_s]), np.stack([x[1] for x in sums_s]),
+                                                    q.free_cells_inv)
+                av_one = one.download_av_vels(warm_s + args.steps)
+                av_same = bool(np.array_equal(av_split.view(np.uint32), av_one.view(np.uint32)))
         barrier()
         strong = {"value": round(strong_mlups, 1), "unit": "MLUPS", "ms_per_step": round(ms_s / args.steps, 5),
                   "grid": f"{nx}x{ny_s}", "rows_per_gpu": rows_s, "kernel": info_s["kernel_name"],
                   "n1_value": round(n1, 1) if n1 else None,
                   "efficiency_vs_n1": round(strong_mlups / (world * n1), 4) if n1 else None,
+                  "av_vels_bitwise_vs_n1": av_same if rank == 0 else None,
                   "note": f"the {nx}x{ny_s} grid of the N = 1 bench split into {world} row slabs, {args.steps} steps, "
                           f"CUDA events, max over ranks; n1_value = the same grid and step count on rank 0's GPU alone, "
-                          f"measured in this run"}
+                          f"measured in this run; av_vels_bitwise_vs_n1: all {warm_s + args.steps} av_vels values of the "
+                          f"split run equal that run's bit for bit"}
+        bad = torch.tensor([1 if (rank == 0 and not av_same) else 0], device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            if rank == 0:
+                print(f"bench.py: STRONG-SPLIT MISMATCH: av_vels of the {world}-slab run differ from the single-GPU run "
+                      f"({info_s['kernel_name']})", file=sys.stderr, flush=True)
+            dist.destroy_process_group()
+            sys.exit(3)
 
     line = None
     if rank == 0:

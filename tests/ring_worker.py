@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--split", default="11,14")  # two run() calls
     ap.add_argument("--fuse2", type=int, default=-1)
+    ap.add_argument("--fuse2-rows", type=int, default=8, help="row-segment length of the two-step kernel; 0: automatic tiling")
     ap.add_argument("--absent-rank", type=int, default=-1,
                     help="this rank never calls lbm_run: its neighbour must report a timeout, not hang")
     ap.add_argument("--mismatch-rank", type=int, default=-1,
@@ -43,7 +44,7 @@ def main():
     if args.mismatch_rank >= 0:
         fuse2 = 0 if rank == args.mismatch_rank else 1
     sim = lbm.cabi.Simulation(p, slab=(local, rank, world, y0, rows),
-                              options={"cells_per_thread": 4, "fuse2": fuse2, "fuse2_rows": 8})
+                              options={"cells_per_thread": 4, "fuse2": fuse2, "fuse2_rows": args.fuse2_rows})
     blobs = [None] * world
     dist.all_gather_object(blobs, sim.export_blob())
     if args.mismatch_rank >= 0:
