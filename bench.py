@@ -135,6 +135,19 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def workload_config(nx, rows, world, scaling="weak"):
+    """`config` of the JSON line: the WORKLOAD only, so that both arms (--impl b200 / reference) print the very same
+    dict; what is specific to an arm (kernel, decomposition, the CPU arm's bounded sample) goes under `run`."""
+    ny_global = rows * world
+    return {
+        "workload": f"synthetic {nx}x{rows} channel per GPU (BASELINE.json configs[4]): "
+                    f"global {nx}x{ny_global}, walls + 64x64 blocks every 1024 cells",
+        "nx": nx, "ny_global": ny_global, "rows_per_gpu": rows, "scaling": scaling,
+        "l2": f"no flush needed: the two lattices are {2 * 36 * nx * rows / 2**30:.1f} GiB per GPU, "
+              f"far larger than the 126 MB L2",
+    }
+
+
 def channel_free_cells(lbm, nx, ny):
     return lbm.decks.synthetic_channel_free_cells(nx, ny)
 
@@ -209,9 +222,8 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * total / len(times), 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {NX}x{ROWS_PER_GPU} channel per GPU (BASELINE configs[4]); "
-                               f"CPU arm steps a bounded {NX}x{ny} sample of it",
-                   "nx": NX, "ny_sample": ny},
+        "config": workload_config(NX, ROWS_PER_GPU, max(1, args.gpus)),
+        "run": {"sample": f"the CPU arm steps a bounded {NX}x{ny} sample of the workload", "ny_sample": ny},
         "cpu_baseline": {"value": round(mlups, 1), "unit": "MLUPS", "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": round(mlups, 1), "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -584,15 +596,11 @@ def run_b200_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5),
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": f"synthetic {nx}x{rows} channel per GPU (BASELINE.json configs[4]): "
-                            f"global {nx}x{ny_global}, walls + 64x64 blocks every 1024 cells",
-                "nx": nx, "ny_global": ny_global, "rows_per_gpu": rows,
+            "config": workload_config(nx, rows, world, args.scaling),
+            "run": {
                 "decomposition": f"{world} row slab(s), one process per GPU, in-kernel halo stores over CUDA-IPC peer "
                                  f"memory ({ring.halo_bytes_per_launch(nx)} B per neighbour per launch), epoch flags",
                 "kernel": kname,
-                "l2": f"no flush needed: the two lattices are {2 * 36 * per_gpu_cells / 2**30:.1f} GiB per GPU, "
-                      f"far larger than the 126 MB L2",
                 "e2e_region": f"upload + {args.steps} steps + sync + download (d2q9-bgk.c:196-263), pinned host buffers",
             },
             "roofline": {

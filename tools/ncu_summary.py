@@ -98,7 +98,7 @@ def main():
     rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
     per_launch = sum(a + b for a, b in zip(rd, wr)) / len(rd)
     kname = data[0][hdr.index("Kernel Name")]
-    # ncu's demangled name -> the name lbm_get_info reports (bench.py's config.kernel)
+    # ncu's demangled name -> the name lbm_get_info reports (bench.py's run.kernel)
     import re
     steps = 1
     m = re.search(r"step_kernel<(\d+), (\d+), (\d+), (\d+), (\d+)>", kname)
