@@ -447,15 +447,24 @@ int ensure_av_capacity(lbm_ctx* ctx, long long need) {
     if (set_device(s)) return 1;
     long long cap = std::max(need, std::max<long long>(s.av_capacity * 2, 1024));
     double *hi = nullptr, *lo = nullptr;
-    CK(cudaMalloc(&hi, sizeof(double) * cap));
-    CK(cudaMalloc(&lo, sizeof(double) * cap));
-    CK(cudaMemsetAsync(hi, 0, sizeof(double) * cap, s.stream));
-    CK(cudaMemsetAsync(lo, 0, sizeof(double) * cap, s.stream));
-    if (s.av_capacity > 0) {
-      CK(cudaMemcpyAsync(hi, s.av_hi, sizeof(double) * s.av_capacity, cudaMemcpyDeviceToDevice, s.stream));
-      CK(cudaMemcpyAsync(lo, s.av_lo, sizeof(double) * s.av_capacity, cudaMemcpyDeviceToDevice, s.stream));
+    auto grow = [&]() -> int {
+      CK(cudaMalloc(&hi, sizeof(double) * cap));
+      CK(cudaMalloc(&lo, sizeof(double) * cap));
+      CK(cudaMemsetAsync(hi, 0, sizeof(double) * cap, s.stream));
+      CK(cudaMemsetAsync(lo, 0, sizeof(double) * cap, s.stream));
+      if (s.av_capacity > 0) {
+        CK(cudaMemcpyAsync(hi, s.av_hi, sizeof(double) * s.av_capacity, cudaMemcpyDeviceToDevice, s.stream));
+        CK(cudaMemcpyAsync(lo, s.av_lo, sizeof(double) * s.av_capacity, cudaMemcpyDeviceToDevice, s.stream));
+      }
+      CK(cudaStreamSynchronize(s.stream));
+      return 0;
+    };
+    if (grow()) {   // keep the old buffers, drop the half-made new ones
+      cudaFree(hi);
+      cudaFree(lo);
+      (void)cudaGetLastError();
+      return 1;
     }
-    CK(cudaStreamSynchronize(s.stream));
     if (s.av_hi) CK(cudaFree(s.av_hi));
     if (s.av_lo) CK(cudaFree(s.av_lo));
     s.av_hi = hi;
@@ -1388,6 +1397,7 @@ int lbm_download_final_state(lbm_ctx* ctx, float* u_x, float* u_y, float* u, flo
   if (!ctx) return fail("ctx is NULL");
   if (!ctx->uploaded) return fail("lbm_download_final_state before lbm_upload");
   DeviceGuard guard;
+  if (check_ring_health(ctx)) return 1;
   float* host[4] = {u_x, u_y, u, pressure};
   const int nx = ctx->p.nx;
   for (auto& s : ctx->slabs) {
@@ -1429,9 +1439,10 @@ int lbm_download_av_sums(lbm_ctx* ctx, double* hi, double* lo, int n) {
   if (n < 0 || n > ctx->steps_since_upload) return fail("asked for %d averages, %lld steps run", n, ctx->steps_since_upload);
   if (ctx->slabs.size() != 1) return fail("lbm_download_av_sums needs a one-slab context");
   DeviceGuard guard;
+  if (n == 0) return 0;
+  if (check_ring_health(ctx)) return 1;
   Slab& s = ctx->slabs[0];
   if (set_device(s)) return 1;
-  if (n == 0) return 0;
   CK(cudaMemcpyAsync(hi, s.av_hi, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaMemcpyAsync(lo, s.av_lo, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
@@ -1460,6 +1471,7 @@ int lbm_download_av_vels(lbm_ctx* ctx, float* av, int n) {
   if (n < 0 || n > ctx->steps_since_upload) return fail("asked for %d averages, %lld steps run", n, ctx->steps_since_upload);
   if (n == 0) return 0;
   DeviceGuard guard;
+  if (check_ring_health(ctx)) return 1;
   const int parts = (int)ctx->slabs.size();
   std::vector<double> hi((size_t)parts * n), lo((size_t)parts * n);
   for (int i = 0; i < parts; i++) {
