@@ -497,6 +497,7 @@ def run_b200_arm(args):
     e2e_runs = [e2e_once(packed=False) for _ in range(3)]
     e2e = min(e2e_runs, key=lambda r: r["seconds"])
     e2e["runs_s"] = [r["seconds"] for r in e2e_runs]
+    e2e["runs_phases_s"] = [[r["upload_s"], r["loop_s"], r["download_s"]] for r in e2e_runs]   # which phase the host noise hit
     checksum = float(out_h[:, ::257, ::263].astype(np.float64).sum())
     if not np.isfinite(checksum):
         raise SystemExit("final state is not finite")
