@@ -186,6 +186,11 @@ def time_oracle(lbm, ny, steps, warmup, variant="fastest"):
     return times, int(lib.oracle_num_threads())
 
 
+def _oracle_build():
+    import oracle_lib
+    return oracle_lib.describe("fastest")
+
+
 def cpu_baseline(lbm, budget_s=15.0):
     """The oracle port on this box's host cores, bounded to ~budget_s of CPU work."""
     ny = 1024
@@ -193,10 +198,17 @@ def cpu_baseline(lbm, budget_s=15.0):
     steps = int(max(3, min(100, budget_s / max(t1[0], 1e-3))))
     times, threads = time_oracle(lbm, ny, steps, 0)
     mlups = NX * ny * len(times) / sum(times) / 1e6
-    return {"value": round(mlups, 1), "unit": "MLUPS", "cores": threads, "kind": "port",
-            "sample": f"{len(times)} time steps of a {NX}x{ny} slab of the same synthetic channel "
-                      f"(oracle/lbm_oracle.c fp32, gcc -O3 -fopenmp -mavx2 if available, "
-                      f"OMP threads = {threads})"}
+    rec = {"value": round(mlups, 1), "unit": "MLUPS", "cores": threads, "kind": "port",
+           "sample": f"{len(times)} time steps of a {NX}x{ny} slab of the same synthetic channel "
+                     f"(oracle/lbm_oracle.c fp32, {_oracle_build()}, OMP threads = {threads})"}
+    # beside it: the same source with the north star's plain flags and the cell-by-cell row loop (SURVEY 8d's recipe)
+    import oracle_lib
+    tp, _ = time_oracle(lbm, ny, 1, 1, variant="base")
+    nplain = int(max(2, min(20, 5.0 / max(tp[0], 1e-3))))
+    tplain, _ = time_oracle(lbm, ny, nplain, 0, variant="base")
+    rec["plain_build"] = {"value": round(NX * ny * len(tplain) / sum(tplain) / 1e6, 1), "steps": len(tplain),
+                          "build": oracle_lib.describe("base")}
+    return rec
 
 
 def run_reference_arm(args):
@@ -216,7 +228,7 @@ def run_reference_arm(args):
     total = sum(times)
     mlups = NX * ny * len(times) / total / 1e6
     sample = (f"each step = one time step (accelerate + fused propagate/rebound/collision/av_vels) of a "
-              f"{NX}x{ny} slab of the synthetic channel on {threads} OpenMP threads")
+              f"{NX}x{ny} slab of the synthetic channel on {threads} OpenMP threads ({_oracle_build()})")
     line = {
         "impl": "reference", "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -703,7 +715,7 @@ def decks_block(lbm, cpu=True):
             oracle_lib.run_f32(p, cells, obstacles, n, reference_order=False, variant="fastest")
             cpu_s = time.perf_counter() - t0
             rec["cpu_oracle"] = {"seconds": round(cpu_s, 3), "mlups": round(p.nx * p.ny * n / cpu_s / 1e6, 1),
-                                 "cores": threads, "kind": "port"}
+                                 "cores": threads, "kind": "port", "build": _oracle_build()}
         out[name] = rec
         log(f"[decks] {name}: {json.dumps(rec)}")
     out["note"] = ("device loop time (CUDA events) of the full deck; l2_gbs_algorithmic = 72 B x updates / loop time (the "

@@ -60,77 +60,89 @@ void oracle_set_num_threads(int n)
 /* kernels.cl:69 — lookup[k][0]: the slot an obstacle cell writes value k to. */
 static const int opposite[NSPEEDS] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
 
-/* kernels.cl:116-198 for one cell.  t[] are the nine gathered values, lmask is
- * obstacle^1.  v[k] is the value the reference stores to plane lookup[k][lmask];
- * the return value is the cell's term of tot_u. */
-static inline float collide_f32(const float t[NSPEEDS], int lmask, float omega, float v[NSPEEDS])
+/* kernels.cl:116-198 for one cell.  t0..t8 are the nine gathered values, lmask is
+ * obstacle^1.  v<k> is the value the reference stores to plane lookup[k][lmask];
+ * speed is the cell's term of tot_u.  (Scalars and a struct of scalars rather than
+ * arrays: the row loop of row_update_f32 must stay vectorisable.) */
+typedef struct {
+  float v0, v1, v2, v3, v4, v5, v6, v7, v8, speed;
+} cell_result;
+
+static inline __attribute__((always_inline)) cell_result collide_f32(float t0, float t1, float t2, float t3, float t4,
+                                                                     float t5, float t6, float t7, float t8,
+                                                                     int lmask, float omega)
 {
   const float ic_sq = 3.0f;                       /* kernels.cl:63 */
   const float w0 = 0.4444444444444444444444f;     /* kernels.cl:65 */
   const float w1 = 0.1111111111111111111111f;     /* kernels.cl:66 */
   const float w2 = 0.0277777777777777777778f;     /* kernels.cl:67 */
+  cell_result out;
 
   /* kernels.cl:119-127 */
-  float densvec = t[0];
-  densvec += t[1];
-  densvec += t[2];
-  densvec += t[3];
-  densvec += t[4];
-  densvec += t[5];
-  densvec += t[6];
-  densvec += t[7];
-  densvec += t[8];
+  float densvec = t0;
+  densvec += t1;
+  densvec += t2;
+  densvec += t3;
+  densvec += t4;
+  densvec += t5;
+  densvec += t6;
+  densvec += t7;
+  densvec += t8;
 
   float densinv = 1.0f / densvec;                 /* kernels.cl:129 */
 
   /* kernels.cl:131-141 (momentum, not velocity) */
-  float u_x = t[1] + t[5];
-  u_x += t[8];
-  u_x -= t[3];
-  u_x -= t[6];
-  u_x -= t[7];
+  float u_x = t1 + t5;
+  u_x += t8;
+  u_x -= t3;
+  u_x -= t6;
+  u_x -= t7;
 
-  float u_y = t[2] + t[5];
-  u_y += t[6];
-  u_y -= t[4];
-  u_y -= t[7];
-  u_y -= t[8];
+  float u_y = t2 + t5;
+  u_y += t6;
+  u_y -= t4;
+  u_y -= t7;
+  u_y -= t8;
 
   float u_sq = fmaf(u_x, u_x, u_y * u_y);         /* kernels.cl:143, contracted */
 
   /* kernels.cl:146-154; uvec[3,4,7,8] are the negatives of uvec[1,2,5,6] */
-  float uvec[NSPEEDS];
-  uvec[1] = u_x;
-  uvec[2] = u_y;
-  uvec[5] = u_x + u_y;
-  uvec[6] = -u_x + u_y;
+  const float uvec1 = u_x;
+  const float uvec2 = u_y;
+  const float uvec5 = u_x + u_y;
+  const float uvec6 = -u_x + u_y;
 
   /* kernels.cl:176-185: `0.5f * densinv*ic_sq` groups as ((0.5f*densinv)*ic_sq) */
   const float half_inv = 0.5f * densinv * ic_sq;
   const float relax = (float)lmask * omega;       /* kernels.cl:187-197: lmask*OMEGA */
-  static const int plus[4] = {1, 2, 5, 6}, minus[4] = {3, 4, 7, 8};
 
   /* d_equ[0] = w0 * (densvec - half_inv*u_sq); v[0] = t[0] + relax*(d_equ[0] - t[0]) */
   {
     const float y = fmaf(-half_inv, u_sq, densvec);
-    const float r = fmaf(w0, y, -t[0]);
-    v[0] = fmaf(relax, r, t[0]);
+    const float r = fmaf(w0, y, -t0);
+    out.v0 = fmaf(relax, r, t0);
   }
-  for (int i = 0; i < 4; i++) {
-    const int kp = plus[i], km = minus[i];
-    const float w = (i < 2) ? w1 : w2;
-    const float u = uvec[kp];
-    /* ic_sqtimesu = u*ic_sq (kernels.cl:156-164); ic_sqtimesu_sq - u_sq = (u*ic_sq)*u - u_sq (:166-185) */
-    const float s = fmaf(u * ic_sq, u, -u_sq);
-    /* d_equ[k] = w * (densvec + ic_sqtimesu[k] + half_inv * s), for +u and for -u */
-    const float yp = fmaf(half_inv, s, fmaf(u, ic_sq, densvec));
-    const float ym = fmaf(half_inv, s, fmaf(u, -ic_sq, densvec));
-    /* v[k] = t[k] + relax * (d_equ[k] - t[k]) */
-    v[kp] = fmaf(relax, fmaf(w, yp, -t[kp]), t[kp]);
-    v[km] = fmaf(relax, fmaf(w, ym, -t[km]), t[km]);
-  }
+  /* the four direction pairs (k, opposite k) = (1,3) (2,4) (5,7) (6,8) */
+#define ORACLE_PAIR(kp, km, w)                                                                          \
+  do {                                                                                                  \
+    const float u = uvec##kp;                                                                           \
+    /* ic_sqtimesu = u*ic_sq (kernels.cl:156-164); ic_sqtimesu_sq - u_sq = (u*ic_sq)*u - u_sq (:166-185) */ \
+    const float s = fmaf(u * ic_sq, u, -u_sq);                                                          \
+    /* d_equ[k] = w * (densvec + ic_sqtimesu[k] + half_inv * s), for +u and for -u */                   \
+    const float yp = fmaf(half_inv, s, fmaf(u, ic_sq, densvec));                                        \
+    const float ym = fmaf(half_inv, s, fmaf(u, -ic_sq, densvec));                                       \
+    /* v[k] = t[k] + relax * (d_equ[k] - t[k]) */                                                       \
+    out.v##kp = fmaf(relax, fmaf(w, yp, -t##kp), t##kp);                                                \
+    out.v##km = fmaf(relax, fmaf(w, ym, -t##km), t##km);                                                \
+  } while (0)
+  ORACLE_PAIR(1, 3, w1);
+  ORACLE_PAIR(2, 4, w1);
+  ORACLE_PAIR(5, 7, w2);
+  ORACLE_PAIR(6, 8, w2);
+#undef ORACLE_PAIR
 
-  return (float)lmask * sqrtf(u_sq) * densinv;    /* kernels.cl:198 */
+  out.speed = (float)lmask * sqrtf(u_sq) * densinv;    /* kernels.cl:198 */
+  return out;
 }
 
 void oracle_f32_accelerate(const oracle_params *p, float *cells, const int *obstacles)
@@ -158,33 +170,80 @@ void oracle_f32_accelerate(const oracle_params *p, float *cells, const int *obst
   }
 }
 
+/* One cell of kernels.cl:91-198 at column xx with the periodic neighbours x_w, x_e. */
+static inline void cell_update_f32(int xx, int x_w, int x_e, float omega, const float *const s[NSPEEDS],
+                                   float *const d[NSPEEDS], const int *obst, float *speed)
+{
+  const int lmask = obst[xx] ^ 1;                                /* kernels.cl:113 */
+  /* kernels.cl:104-112 */
+  const cell_result r = collide_f32(s[0][xx], s[1][x_w], s[2][xx], s[3][x_e], s[4][xx], s[5][x_w], s[6][x_e],
+                                    s[7][x_e], s[8][x_w], lmask, omega);
+  const float v[NSPEEDS] = {r.v0, r.v1, r.v2, r.v3, r.v4, r.v5, r.v6, r.v7, r.v8};
+  speed[xx] = r.speed;
+  if (lmask) {
+    for (int k = 0; k < NSPEEDS; k++) d[k][xx] = v[k];            /* lookup[k][1] = k */
+  } else {
+    for (int k = 0; k < NSPEEDS; k++) d[opposite[k]][xx] = v[k];  /* lookup[k][0] */
+  }
+}
+
 /* One row of kernels.cl:91-198.  s_*: source rows (already offset to the
  * row the pull reads: own row for 0,1,3; south row for 2,5,6; north row for
- * 4,7,8), d[k]: destination rows, speed[x] gets the cell's tot_u term. */
+ * 4,7,8), d[k]: destination rows, speed[x] gets the cell's tot_u term.
+ *
+ * ORACLE_SCALAR_ROWS (liboracle.so): the cell-by-cell form above for every column.
+ * Otherwise (the -mavx2 / -mavx512f builds, the CPU baseline): the same cells with the same
+ * operations in the same order, written so that the compiler can run 8 / 16 columns at a time:
+ * the two wrap columns (kernels.cl:100-102) cell by cell, the interior with x_w = xx-1, x_e = xx+1
+ * and the store slot chosen by a select (`d[opposite[k]] = v[k]` for every k is `d[k] =
+ * v[opposite[k]]` for every k, the table being an involution).  Vector add / mul / fma / div / sqrt
+ * are the same correctly rounded IEEE operations lane by lane, so the two forms agree bit for bit
+ * (tests/test_oracle_goldens.py compares the builds). */
+#ifndef ORACLE_SCALAR_ROWS
+static void row_interior_f32(int lo, int hi, float omega, const float *const s[NSPEEDS], float *const d[NSPEEDS],
+                             const int *obst, float *speed)
+{
+  /* columns [lo, hi), 1 <= lo, hi <= nx-1 */
+  const float *restrict s0 = s[0], *restrict s1 = s[1], *restrict s2 = s[2], *restrict s3 = s[3],
+              *restrict s4 = s[4], *restrict s5 = s[5], *restrict s6 = s[6], *restrict s7 = s[7],
+              *restrict s8 = s[8];
+  float *restrict d0 = d[0], *restrict d1 = d[1], *restrict d2 = d[2], *restrict d3 = d[3], *restrict d4 = d[4],
+        *restrict d5 = d[5], *restrict d6 = d[6], *restrict d7 = d[7], *restrict d8 = d[8];
+  const int *restrict ob = obst;
+  float *restrict sp = speed;
+#pragma omp simd
+  for (int xx = lo; xx < hi; xx++) {
+    const int lmask = ob[xx] ^ 1;
+    const cell_result r = collide_f32(s0[xx], s1[xx - 1], s2[xx], s3[xx + 1], s4[xx], s5[xx - 1], s6[xx + 1],
+                                      s7[xx + 1], s8[xx - 1], lmask, omega);
+    sp[xx] = r.speed;
+    d0[xx] = r.v0;
+    d1[xx] = lmask ? r.v1 : r.v3;
+    d2[xx] = lmask ? r.v2 : r.v4;
+    d3[xx] = lmask ? r.v3 : r.v1;
+    d4[xx] = lmask ? r.v4 : r.v2;
+    d5[xx] = lmask ? r.v5 : r.v7;
+    d6[xx] = lmask ? r.v6 : r.v8;
+    d7[xx] = lmask ? r.v7 : r.v5;
+    d8[xx] = lmask ? r.v8 : r.v6;
+  }
+}
+#endif
+
 static void row_update_f32(int nx, float omega, const float *const s[NSPEEDS], float *const d[NSPEEDS],
                            const int *obst, float *speed)
 {
+#ifdef ORACLE_SCALAR_ROWS
   for (int xx = 0; xx < nx; xx++) {
     const int x_e = (xx + 1 >= nx) ? xx + 1 - nx : xx + 1;      /* kernels.cl:100-101 */
     const int x_w = (xx == 0) ? nx - 1 : xx - 1;                /* kernels.cl:102 */
-    float t[NSPEEDS], v[NSPEEDS];
-    t[0] = s[0][xx];                                             /* kernels.cl:104-112 */
-    t[1] = s[1][x_w];
-    t[2] = s[2][xx];
-    t[3] = s[3][x_e];
-    t[4] = s[4][xx];
-    t[5] = s[5][x_w];
-    t[6] = s[6][x_e];
-    t[7] = s[7][x_e];
-    t[8] = s[8][x_w];
-    const int lmask = obst[xx] ^ 1;                              /* kernels.cl:113 */
-    speed[xx] = collide_f32(t, lmask, omega, v);
-    if (lmask) {
-      for (int k = 0; k < NSPEEDS; k++) d[k][xx] = v[k];          /* lookup[k][1] = k */
-    } else {
-      for (int k = 0; k < NSPEEDS; k++) d[opposite[k]][xx] = v[k]; /* lookup[k][0] */
-    }
+    cell_update_f32(xx, x_w, x_e, omega, s, d, obst, speed);
   }
+#else
+  cell_update_f32(0, nx - 1, (nx > 1) ? 1 : 0, omega, s, d, obst, speed);
+  if (nx > 1) cell_update_f32(nx - 1, nx - 2, 0, omega, s, d, obst, speed);
+  row_interior_f32(1, nx - 1, omega, s, d, obst, speed);
+#endif
 }
 
 static int is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }

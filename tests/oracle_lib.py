@@ -36,24 +36,48 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def _cpu_has_avx2() -> bool:
+def _cpu_has(flag: str) -> bool:
     try:
         with open("/proc/cpuinfo") as fp:
-            return " avx2 " in fp.read().replace("\n", " ")
+            return f" {flag} " in fp.read().replace("\n", " ") + " "
     except OSError:
         return False
+
+
+def _cpu_has_avx2() -> bool:
+    return _cpu_has("avx2") and _cpu_has("fma")
+
+
+def _cpu_has_avx512() -> bool:
+    return _cpu_has_avx2() and _cpu_has("avx512f") and _cpu_has("avx512vl")
+
+
+def fastest_variant() -> str:
+    """The widest build this CPU runs: 'avx512', 'avx2' or 'base'."""
+    return "avx512" if _cpu_has_avx512() else "avx2" if _cpu_has_avx2() else "base"
+
+
+def describe(variant: str) -> str:
+    """How a build was made, for the bench records."""
+    if variant == "fastest":
+        variant = fastest_variant()
+    common = "gcc -O3 -fopenmp -mfma -ffp-contract=off"
+    return {"base": f"{common}, cell-by-cell row loop",
+            "avx2": f"{common} -mavx2, vectorised row loop (8 columns per instruction)",
+            "avx512": f"{common} -mavx512f, vectorised row loop (16 columns per instruction)"}[variant]
 
 
 _lib_cache = {}
 
 
 def load(variant: str = "base"):
-    """variant: 'base' (-O3 -fopenmp, the north-star baseline flags), 'avx2', or 'fastest'."""
+    """variant: 'base' (-O3 -fopenmp, the north-star baseline flags, cell-by-cell row loop), 'avx2' / 'avx512'
+    (the vectorisable row loop, bit-identical results), or 'fastest' (the widest this CPU runs)."""
     if variant == "fastest":
-        variant = "avx2" if _cpu_has_avx2() else "base"
+        variant = fastest_variant()
     if variant in _lib_cache:
         return _lib_cache[variant]
-    name = {"base": "liboracle.so", "avx2": "liboracle_avx2.so"}[variant]
+    name = {"base": "liboracle.so", "avx2": "liboracle_avx2.so", "avx512": "liboracle_avx512.so"}[variant]
     path = os.path.join(ORACLE_DIR, name)
     if not os.path.exists(path):
         build_oracle()

@@ -80,15 +80,29 @@ def test_reference_order_and_sequential_sums_agree(oracle):
     np.testing.assert_allclose(av1, av2, rtol=2e-6)
 
 
-def test_oracle_variants_bit_identical(oracle):
-    """-O3 and -O3 -mavx2 builds (both -ffp-contract=off) give the same bits."""
-    p, cells, obstacles = helpers.random_case(192, 40, seed=2)
-    c1, av1 = oracle.run_f32(p, cells, obstacles, 5, variant="base")
-    try:
-        c2, av2 = oracle.run_f32(p, cells, obstacles, 5, variant="avx2")
-    except OSError:
-        pytest.skip("avx2 build not loadable here")
-    assert np.array_equal(helpers.bits(c1), helpers.bits(c2)) and np.array_equal(helpers.bits(av1), helpers.bits(av2))
+@pytest.mark.parametrize("variant", ["avx2", "avx512"])
+def test_oracle_variants_bit_identical(oracle, variant):
+    """liboracle.so walks a row cell by cell (the line-by-line restatement); the -mavx2 / -mavx512f builds
+    run the interior columns 8 / 16 at a time with the store slot picked by a select (the CPU baseline of
+    bench.py).  Same operations in the same order, so the same bits: lattice and av_vels, for ragged and
+    tiny widths, open and walled channels, both av_vels orders, and cells holding signed zeros."""
+    if variant == "avx512" and not oracle._cpu_has_avx512():
+        pytest.skip("this CPU has no AVX-512")
+    if not oracle._cpu_has_avx2():
+        pytest.skip("this CPU has no AVX2")
+    shapes = [(1, 2), (2, 3), (3, 5), (7, 4), (9, 3), (17, 9), (33, 12), (128, 8), (130, 7), (192, 40), (300, 11)]
+    for i, (nx, ny) in enumerate(shapes):
+        walls = ny >= 4 and i % 2 == 0
+        p, cells, obstacles = helpers.random_case(nx, ny, seed=2 + i, walls=walls)
+        if nx >= 7:   # signed zeros: relax * r + t with relax = 0 in obstacle cells must keep what the scalar form gives
+            cells[3, ny // 2, 2] = -0.0
+            cells[7, 0, nx - 1] = 0.0
+            obstacles[ny // 2, 1] = 1
+        for ref_order in (True, False):
+            c1, av1 = oracle.run_f32(p, cells, obstacles, 6, reference_order=ref_order, variant="base")
+            c2, av2 = oracle.run_f32(p, cells, obstacles, 6, reference_order=ref_order, variant=variant)
+            assert np.array_equal(helpers.bits(c1), helpers.bits(c2)), (nx, ny, ref_order)
+            assert np.array_equal(helpers.bits(av1), helpers.bits(av2)), (nx, ny, ref_order)
 
 
 def test_mass_conservation_and_obstacle_permutation(oracle):
