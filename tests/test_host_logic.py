@@ -245,3 +245,25 @@ def test_synthetic_channel_rows_tile_the_deck():
     assert obstacles[0].all() and obstacles[-1].all() and not obstacles[3072 - 2].any()
     frac = obstacles[1:-1].mean()
     assert 0.003 < frac < 0.005      # 64x64 blocks every 1024 cells: ~0.4 %
+
+
+def test_reference_arm_line_and_shared_config():
+    """bench.py --impl reference runs on host cores alone and prints ONE JSON line whose `config` is the
+    very dict the B200 arm prints for the same --gpus (the workload only; arm-specific details live under
+    `run`), with the e2e / cpu_baseline keys the bench contract asks of the reference arm."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                           "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "MLUPS" and line["unit"] == "MLUPS"
+    assert line["config"] == bench.workload_config(bench.NX, bench.ROWS_PER_GPU, 1)
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["gpu_launches"] == 0
