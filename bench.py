@@ -223,7 +223,7 @@ def run_reference_arm(args):
     t_probe, threads = time_oracle(lbm, 256, 1, 1)
     rate = NX * 256 / t_probe[0]  # cells per second
     budget = 120.0 / max(1, args.steps + args.warmup)
-    ny = int(max(64, min(ROWS_PER_GPU, (rate * budget / NX) // 64 * 64)))
+    ny = int(max(64, min(ROWS_PER_GPU, args.ref_rows, (rate * budget / NX) // 64 * 64)))
     times, threads = time_oracle(lbm, ny, args.steps, args.warmup)
     total = sum(times)
     mlups = NX * ny * len(times) / total / 1e6
@@ -737,6 +737,8 @@ def main():
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="weak (default, the driver's contract): rows-per-gpu rows on every GPU; "
                          "strong: rows-per-gpu rows in total, split over the GPUs")
+    ap.add_argument("--ref-rows", type=int, default=ROWS_PER_GPU,
+                    help="--impl reference: at most this many rows in the CPU arm's per-step sample (tests use a small one)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true",
                     help="N > 1: skip the ring-vs-oracle bitwise pre-flight (development only)")

@@ -255,8 +255,8 @@ def test_reference_arm_line_and_shared_config():
     import sys
     sys.path.insert(0, ROOT)
     import bench
-    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                           "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                           "--warmup", "1", "--ref-rows", "1024"], capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stderr[-2000:]
     lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
